@@ -1,0 +1,249 @@
+/*
+ * roc_b200.h — C ABI of the B200-native kernel layer for ROC's GCN-training path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its
+ * device code is reached through Legion task variants
+ *   static void X::forward_task(const Task*, const std::vector<PhysicalRegion>&, Context, Runtime*)
+ * (gnn.h:224-349, registered gnn.cc:241-426).  Every entry point below replaces
+ * the CUDA work one of those tasks did; the comment on each cites the task /
+ * kernel / library call it stands in for.  INTEGRATION.md shows the stub a ROC
+ * maintainer adds inside each *_task to call it.
+ *
+ * Conventions
+ *  - plain C, no torch / Legion types; all data pointers are DEVICE pointers
+ *    unless a name says `host`; caller owns every buffer;
+ *  - `roc_stream_t` is a `cudaStream_t`; calls enqueue work and return (no
+ *    device sync) unless documented otherwise;
+ *  - return value: 0 = ROC_OK; > 0 = a cudaError_t; < 0 = ROC_ERR_*;
+ *  - node tensors are row-major [rows][ld] fp32 with `ld >= H` floats between
+ *    rows (the reference's layout is ld == H, gnn.cc:480-486).  The vectorised
+ *    paths need ld % 4 == 0 and 16-byte aligned bases; other shapes take a
+ *    scalar path.  Columns H..ld-1 are never read or written;
+ *  - graph ids follow types.h:5-15: V_ID = uint32, E_ID = uint64;
+ *    rowEnd[v-rowLeft] is the GLOBAL END offset of v's in-edge list
+ *    (NodeStruct.index, load_task.cu:283-288), the first local row starts at
+ *    colLeft (scattergather_kernel.cu:46-50); colSrc[e-colLeft] is the source
+ *    vertex of edge e (EdgeStruct.src; the redundant .dst is dropped).
+ */
+#ifndef ROC_B200_H_
+#define ROC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint32_t roc_vid_t;   /* V_ID,  types.h:5 */
+typedef uint64_t roc_eid_t;   /* E_ID,  types.h:6 */
+typedef void*    roc_stream_t; /* cudaStream_t */
+
+#define ROC_OK               0
+#define ROC_ERR_INVALID     (-1)  /* bad argument (NULL pointer, negative size ...) */
+#define ROC_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels handle */
+#define ROC_ERR_NOMEM       (-3)
+#define ROC_ERR_NO_DEVICE   (-4)  /* no CUDA device: the product has no CPU fallback */
+#define ROC_ERR_IO          (-5)
+
+/* ActiMode, gnn.h:82-86 */
+#define ROC_AC_MODE_NONE    0
+#define ROC_AC_MODE_RELU    1
+#define ROC_AC_MODE_SIGMOID 2
+
+/* MaskType, gnn.h:98-103 */
+#define ROC_MASK_TRAIN 0
+#define ROC_MASK_VAL   1
+#define ROC_MASK_TEST  2
+#define ROC_MASK_NONE  3
+
+/* epilogue fused into the ScatterGather store (what the model applies right
+ * after it, gnn.cc:83-85): NORM = the following indegree_norm, RELU = the relu
+ * after that.  Applied in that order. */
+#define ROC_SG_EPI_NONE 0
+#define ROC_SG_EPI_NORM 1
+#define ROC_SG_EPI_RELU 2
+
+/* PerfMetrics, softmax_kernel.cu:35-39 (same field order) */
+typedef struct {
+  float trainLoss;
+  int trainAll, testAll, valAll, trainCorrect, testCorrect, valCorrect;
+} roc_perf_metrics;
+
+const char* roc_version(void);
+/* Number of usable CUDA devices (0 if none); never fails. */
+int roc_device_count(void);
+/* Total kernels this library has launched in this process (for bench's gpu_launches). */
+uint64_t roc_launch_count(void);
+
+/* ---------------------------------------------------------------- graph --- */
+
+/* Replaces Graph::Graph's partition loop, gnn.cc:806-829 + 852-870 (HOST code,
+ * host pointers).  Greedy edge-balanced contiguous vertex ranges; a range is
+ * closed when its in-edge count exceeds ceil(E/P) (strict).  vbounds[2c..2c+1] =
+ * [left,right] inclusive, ebounds[2c..2c+1] = [lo,hi] inclusive.  Returns the
+ * number of ranges produced in *numRanges; the reference asserts it equals
+ * numParts (gnn.cc:829) — here that case returns ROC_ERR_UNSUPPORTED after
+ * filling what fits. */
+int roc_partition(roc_vid_t numNodes, roc_eid_t numEdges, int numParts,
+                  const roc_eid_t* host_rowEnd, roc_vid_t* host_vbounds,
+                  roc_eid_t* host_ebounds, int* numRanges);
+
+/* Replaces init_graph_kernel, load_task.cu:271-294.  From the partition's raw
+ * slices (rawRows = global END offsets of local rows, rawCols = sources) writes
+ *   rowPtrs[n]  = rawRows[n]                          (NodeStruct, u64)     if non-NULL
+ *   edgeStructs = {src = rawCols[e], dst = n+rowLeft} (EdgeStruct, 2 x u32) if non-NULL
+ *   colSrc[e]   = rawCols[e]                          (lean u32 layout)     if non-NULL */
+int roc_build_csr(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft,
+                  const roc_eid_t* rawRows, const roc_vid_t* rawCols,
+                  roc_eid_t* rowPtrs, roc_vid_t* edgeStructs, roc_vid_t* colSrc,
+                  roc_stream_t stream);
+
+/* -------------------------------------------------------- ScatterGather --- */
+
+/* A plan holds the edge-balanced schedule for one partition's CSR: 64-edge
+ * chunks, the first row of each chunk, carry slots for rows longer than a
+ * chunk.  It is a private, derived structure; rowEnd/colSrc stay the canonical
+ * CSR and must outlive the plan.  Creation synchronises the stream. */
+typedef struct roc_sg_plan roc_sg_plan;
+
+int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft,
+                       const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
+                       roc_stream_t stream, roc_sg_plan** plan);
+/* Pre-size the carry workspace for feature widths up to maxH (otherwise it is
+ * grown — with a device synchronisation — by the first call that needs it). */
+int roc_sg_plan_reserve(roc_sg_plan* plan, int maxH);
+void roc_sg_plan_destroy(roc_sg_plan* plan);
+/* Introspection for tests / DESIGN.md numbers. */
+int roc_sg_plan_info(const roc_sg_plan* plan, uint64_t* numChunks,
+                     uint64_t* numCarries, uint64_t* numHeavyRows);
+
+/* Replaces aggre_coop_kernel + ScatterGather::forward_task,
+ * scattergather_kernel.cu:20-76, 78-158:
+ *   out[v-rowLeft][h] = sum_{e in in(v)} in[colSrc[e]][h],  h < H
+ * `in` is indexed by whatever ids colSrc holds (global ids over the whole
+ * [N][ldIn] matrix as in scattergather.cc:69-73, or local+halo ids).
+ * Deterministic: the per-row summation order is fixed by the plan. */
+int roc_sg_forward_planned(const roc_sg_plan* plan, int H, const float* in,
+                           int64_t ldIn, float* out, int64_t ldOut, int epilogue,
+                           roc_stream_t stream);
+
+/* Plan-less form with exactly the reference kernel's argument list
+ * (scattergather_kernel.cu:21-28, EdgeStruct.dst dropped), dense ld == H.
+ * Builds and frees a plan internally (synchronises); use the planned form in
+ * loops. */
+int roc_sg_forward(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, int H,
+                   const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
+                   const float* in, float* out, roc_stream_t stream);
+/* Replaces ScatterGather::backward_task, scattergather_kernel.cu:160-170: the
+ * identical computation on gradients (A, not A^T — quirk Q1). */
+int roc_sg_backward(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, int H,
+                    const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
+                    const float* outGrad, float* inGrad, roc_stream_t stream);
+
+/* ---------------------------------------------------------- elementwise --- */
+
+/* Replaces norm_coop_kernel, graphnorm_kernel.cu:19-57 (fwd and bwd :126-136):
+ * out[n][h] = in[n][h] / sqrtf((float)deg(n)); in/out are the partition's rows.
+ * If `also_relu_mask_of` is non-NULL (fused backward of relu∘norm, gnn.cc:84-85):
+ * out = (also_relu_mask_of > 0 ? in : 0) / sqrtf(deg); it has `in`'s shape and
+ * leading dimension (it is the relu output whose gradient `in` is). */
+int roc_indegree_norm(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, int H,
+                      const roc_eid_t* rowEnd, const float* in, int64_t ldIn,
+                      float* out, int64_t ldOut, const float* also_relu_mask_of,
+                      roc_stream_t stream);
+
+/* Replaces cudnnActivationForward/Backward, activation_kernel.cu:64-66, 128-132.
+ * bwd: dX (+)= dY * f'(.) evaluated from the OUTPUT y; accumulate != 0 adds
+ * into dX (the reference's beta = 1 on a loaded buffer, gnn.cc:704-713). */
+int roc_activation_fwd(int64_t rows, int H, int mode, const float* x, int64_t ldX,
+                       float* y, int64_t ldY, roc_stream_t stream);
+int roc_activation_bwd(int64_t rows, int H, int mode, const float* y, int64_t ldY,
+                       const float* dY, int64_t ldDY, float* dX, int64_t ldDX,
+                       int accumulate, roc_stream_t stream);
+
+/* Replaces op_kernel (EW_TYPE_ADD), element_kernel.cu:19-39, and its backward
+ * add_kernel pair, :93-101. */
+int roc_add_fwd(int64_t rows, int H, const float* a, int64_t ldA, const float* b,
+                int64_t ldB, float* y, int64_t ldY, roc_stream_t stream);
+int roc_add_bwd(int64_t rows, int H, const float* dY, int64_t ldDY, float* dA,
+                int64_t ldDA, int accA, float* dB, int64_t ldDB, int accB,
+                roc_stream_t stream);
+
+/* Replaces cudnnDropoutForward/Backward, dropout_kernel.cu:98-99, 149-150.
+ * y = keep ? x / (1 - rate) : 0.  cuDNN's generator is not reproducible, so the
+ * mask is defined here instead: element (globalRow, h) of a width-H tensor has
+ * dense index k = globalRow*H + h and keeps iff word (k & 3) of
+ * Philox4x32-10(counter = {k>>2 lo, k>>2 hi, step, 0}, key = {seed lo, seed hi})
+ * >= rate * 2^32.  The mask is recomputed in bwd (no reserve space).
+ * `firstRow` = global index of the slab's first row (rowLeft). */
+int roc_dropout_fwd(int64_t rows, int H, int64_t firstRow, float rate, uint64_t seed,
+                    uint32_t step, const float* x, int64_t ldX, float* y, int64_t ldY,
+                    roc_stream_t stream);
+int roc_dropout_bwd(int64_t rows, int H, int64_t firstRow, float rate, uint64_t seed,
+                    uint32_t step, const float* dY, int64_t ldDY, float* dX,
+                    int64_t ldDX, roc_stream_t stream);
+
+/* Replaces SoftmaxCrossEntropy::backward_task, softmax_kernel.cu:81-171:
+ * cudnnSoftmaxForward(ACCURATE) -> calc_loss (:41-79) -> softmax_backward
+ * (:19-33) in ONE kernel.  `labels` is the one-hot fp32 [rows][ldL] tensor the
+ * reference loads (load_task.cu:118-123); `mask` is int32 per row.
+ * `perf` (device, may be NULL) is ACCUMULATED into (zero it first). */
+int roc_softmax_xent_bwd(int64_t rows, int C, const float* logits, int64_t ldZ,
+                         const float* labels, int64_t ldL, const int32_t* mask,
+                         float* grad, int64_t ldG, roc_perf_metrics* perf,
+                         roc_stream_t stream);
+
+/* Same computation with compact labels: labelIdx[v] = class index (what
+ * load_task.cu:118-123 expands to one-hot); 4 B/row instead of 4C B/row. */
+int roc_softmax_xent_bwd_idx(int64_t rows, int C, const float* logits, int64_t ldZ,
+                             const int32_t* labelIdx, const int32_t* mask, float* grad,
+                             int64_t ldG, roc_perf_metrics* perf, roc_stream_t stream);
+
+/* --------------------------------------------------------------- Linear --- */
+
+/* Replaces cublasSgemm in Linear::forward_task, linear_kernel.cu:76-80 (+ the
+ * optional in-place ReLU :83-104):  Y[v][o] = sum_i X[v][i] * W[o*inDim + i].
+ * W is the reference's column-major [inDim][outDim] weight (ld = inDim, Q6).
+ * flags: ROC_LINEAR_NORM_EPILOGUE divides row v by sqrtf(deg(v)) (fuses the
+ * indegree_norm that follows linear in the model, gnn.cc:81-82); then needs
+ * rowLeft-relative rowEnd/colLeft (else pass NULL/0). */
+#define ROC_LINEAR_NORM_EPILOGUE 1
+int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                   const float* W, float* Y, int64_t ldY, int activation, int flags,
+                   const roc_eid_t* rowEnd, roc_eid_t colLeft, roc_stream_t stream);
+
+/* Replaces Linear::backward_task, linear_kernel.cu:129-245:
+ *   if activation == RELU: dY = (Y > 0) ? dY : 0 in place (reluBackward :120-127)
+ *   dW[o*inDim+i] += sum_v X[v][i] * dY[v][o]        (sgemm beta = 1, :220-224)
+ *   dX[v][i] (+)= sum_o W[o*inDim+i] * dY[v][o]       (:227-231) — skipped when
+ *   dX == NULL (leaf input, quirk Q8); accumulate_dX selects += vs =.
+ * `workspace` holds split-K partials of dW; size from roc_linear_bwd_workspace_bytes. */
+size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int outDim);
+int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                   const float* W, const float* Y, int64_t ldY, float* dY,
+                   int64_t ldDY, float* dW, float* dX, int64_t ldDX,
+                   int activation, int accumulate_dX, void* workspace,
+                   size_t workspaceBytes, roc_stream_t stream);
+
+/* ------------------------------------------------------------ optimizer --- */
+
+/* Replaces adam_update, optimizer_kernel.cu:43-63 (launch :98-101).  alpha_t is
+ * the bias-corrected step computed on the host in double (optimizer.cc:79-85).
+ * The reference first sums per-GPU replicas g0 += g_i (:88-94); here WGrad is
+ * already the all-reduced gradient. */
+int roc_adam_update(int64_t count, float alpha_t, float beta1, float beta2,
+                    float weight_decay, float epsilon, const float* WGrad, float* M,
+                    float* V, float* W, roc_stream_t stream);
+
+/* Replaces GlorotUniform::init_task's scale_kernel, initializer_kernel.cu:46-47 +
+ * cuda_helper.cu:2-9: W = (b - a) * u + a over `count` uniforms already in W. */
+int roc_scale(int64_t count, float a, float b, float* W, roc_stream_t stream);
+/* Replaces assign_kernel, cuda_helper.cu:11-18 (zero_grad_task_impl,
+ * ZerosInitializer): 2-D fill of the [rows][H] window of a [rows][ld] tensor. */
+int roc_fill(int64_t rows, int H, float value, float* x, int64_t ld, roc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROC_B200_H_ */

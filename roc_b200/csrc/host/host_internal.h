@@ -1,0 +1,88 @@
+// host_internal.h — internals of the thin C++ host (not part of the public API).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "roc_gnn.h"
+
+namespace roc {
+namespace host {
+
+// FatalError / checkCUDA of the reference (cuda_helper.h:6-29): print and exit(1).
+[[noreturn]] void fatal(const char* what, const char* file, int line);
+#define ROC_FATAL(msg) ::roc::host::fatal((msg), __FILE__, __LINE__)
+#define ROC_CHECK(call)                                                            \
+  do {                                                                             \
+    int rc_ = (int)(call);                                                         \
+    if (rc_ != 0) {                                                                \
+      char b_[640];                                                                \
+      snprintf(b_, sizeof(b_), "%s failed with code %d", #call, rc_);              \
+      ROC_FATAL(b_);                                                               \
+    }                                                                              \
+  } while (0)
+#define ROC_ASSERT(cond)                                                           \
+  do { if (!(cond)) ROC_FATAL("assertion failed: " #cond); } while (0)
+
+struct TensorImpl {
+  int64_t rows = 0;       // local rows (node tensors) or outDim (weights)
+  int H = 0;              // logical width (node: hidden; weight: inDim, stored [out][in])
+  int64_t ld = 0;         // floats between rows (H rounded up to 4 for node tensors)
+  bool isInt = false;     // create_node_tensor<int> (mask)
+  bool isWeight = false;
+  bool requiresGrad = false;
+  bool produced = false;  // output of some op
+  float* data = nullptr;  // lazily allocated (node tensors)
+  float* grad = nullptr;
+  int32_t* labelIdx = nullptr;   // compact labels when loaded through load_labels / set_labels
+};
+
+// NCCL through dlopen so the library has no link-time NCCL dependency and, inside
+// a torch process, binds to the libnccl.so.2 torch already loaded.
+struct Comm {
+  void* lib = nullptr;
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  bool load();
+  static bool unique_id(unsigned char id[128]);
+  bool init(int rank, int world, const unsigned char id[128]);
+  // recvbuf[offsets[r] .. +counts[r]) <- rank r's sendbuf (counts in floats)
+  int allgatherv(const float* sendbuf, float* recvbuf, const std::vector<size_t>& counts,
+                 const std::vector<size_t>& offsets, cudaStream_t st);
+  int allreduce_sum(float* buf, size_t count, cudaStream_t st);
+  int allreduce_sum_i32(int* buf, size_t count, cudaStream_t st);
+  void destroy();
+};
+
+struct RuntimeImpl {
+  int device = 0, myPart = 0, numParts = 1;
+  cudaStream_t stream = nullptr;
+  std::vector<TensorImpl> tensors;
+  std::vector<void*> allocs;
+  Comm comm;
+  bool commReady = false;
+  // shared scratch
+  float* gatherBuf = nullptr; size_t gatherFloats = 0;   // [numNodes][maxLd] when numParts > 1
+  void* linWs = nullptr; size_t linWsBytes = 0;           // split-K workspace of Linear backward
+  float* flatGrad = nullptr; size_t flatGradCount = 0;    // all dW, one all-reduce
+  roc_perf_metrics* d_perf = nullptr;
+  roc_perf_metrics h_perf{};
+  uint32_t trainStep = 0;
+
+  void* dmalloc(size_t bytes);
+  void dfree_all();
+  int new_tensor(int64_t rows, int H, int64_t ld, bool isInt, bool isWeight);
+  float* data(int region);   // allocates on first use, zero-filled
+  float* grad(int region);
+  TensorImpl& t(int region) { return tensors[(size_t)region]; }
+  void ensure_gather(size_t floats);
+  void ensure_lin_ws(size_t bytes);
+};
+
+inline int64_t round_up4(int64_t x) { return (x + 3) / 4 * 4; }
+
+}  // namespace host
+}  // namespace roc

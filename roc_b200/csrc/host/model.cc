@@ -1,0 +1,748 @@
+// model.cc — Model, the op classes, AdamOptimizer, initializers, dataset loaders.
+// Mirrors gnn.cc:433-749 and the per-op .cc files of the reference; each op's
+// forward/backward enqueues C-ABI kernels (roc_b200.h) on the Runtime's stream
+// instead of launching a Legion index task.
+#include <curand.h>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <set>
+#include <sstream>
+
+#include "host_internal.h"
+
+using namespace roc::host;
+
+// roc_softmax_xent_bwd_idx is declared in roc_b200.h
+
+// ------------------------------------------------------------------ GnnOp ---
+// gnn.cc:433-465
+GnnOp::GnnOp(const Tensor& _input) : numInputs(1), numOutputs(0), fusedInto(-1) {
+  inputs[0] = _input;
+  trainableInputs[0] = true;
+  resetInputGrads[0] = true;
+}
+GnnOp::GnnOp(const Tensor& _input1, const Tensor& _input2) : numInputs(2), numOutputs(0), fusedInto(-1) {
+  inputs[0] = _input1; inputs[1] = _input2;
+  for (int i = 0; i < 2; i++) { trainableInputs[i] = true; resetInputGrads[i] = true; }
+}
+GnnOp::GnnOp(const Tensor& _input1, const Tensor& _input2, const Tensor& _input3)
+    : numInputs(3), numOutputs(0), fusedInto(-1) {
+  inputs[0] = _input1; inputs[1] = _input2; inputs[2] = _input3;
+  for (int i = 0; i < 3; i++) { trainableInputs[i] = true; resetInputGrads[i] = true; }
+}
+
+// ------------------------------------------------------------------ Model ---
+Model::Model(const Graph& _graph, Context _ctx, Runtime* _runtime)
+    : mode(MD_MODE_TRAIN), myGraph(_graph), ctx(_ctx), runtime(_runtime), optimizer(NULL), epoch_num(0),
+      fuse(true), printMetrics(true) {}
+
+// gnn.cc:475-532: node tensor = [numNodes][H]; this process holds its vertex range.
+template <>
+Tensor Model::create_node_tensor<DATATYPE>(int _numHidden) const {
+  Tensor t(Tensor::NODE_TENSOR);
+  t.numDim = 2;
+  t.dims[0] = _numHidden;
+  t.dims[1] = myGraph.numNodes;
+  t.region = ctx->new_tensor(local_rows(), _numHidden, round_up4(_numHidden), false, false);
+  return t;
+}
+template <>
+Tensor Model::create_node_tensor<int>(int _numHidden) const {
+  Tensor t(Tensor::NODE_TENSOR);
+  t.numDim = 2;
+  t.dims[0] = _numHidden;
+  t.dims[1] = myGraph.numNodes;
+  t.region = ctx->new_tensor(local_rows(), _numHidden, _numHidden, true, false);
+  return t;
+}
+
+// gnn.cc:591-623: weight [inDim][outDim] (dim0 = inDim fastest => W_mem[o*inDim + i]).
+// The reference keeps one dW replica per GPU inside one region; here each process
+// owns its replica and replicas are summed by one NCCL all-reduce (Model::update).
+Tensor Model::create_weight_tensor(int _inDim, int _outDim, Initializer* initializer) const {
+  Tensor w(Tensor::WEIGHT_TENSOR);
+  w.numDim = 2;
+  w.dims[0] = _inDim;
+  w.dims[1] = _outDim;
+  w.region = ctx->new_tensor(_outDim, _inDim, _inDim, false, true);
+  ctx->t(w.region).requiresGrad = true;
+  if (initializer == NULL) {
+    GlorotUniform glorot;   // default initializer, gnn.cc:614-618
+    glorot.init(this, &w);
+  } else {
+    initializer->init(this, &w);
+  }
+  return w;
+}
+
+Tensor Model::add(const Tensor& a, const Tensor& b) {
+  GnnOp* op = new Element(*this, a, b, EW_TYPE_ADD);
+  layers.push_back(op);
+  return op->outputs[0];
+}
+Tensor Model::dropout(const Tensor& _input, float rate, int seed) {
+  Dropout* op = new Dropout(*this, _input, rate, seed);
+  op->opIndex = (int)layers.size();
+  layers.push_back(op);
+  return op->outputs[0];
+}
+Tensor Model::scatter_gather(const Tensor& _input) {
+  GnnOp* op = new ScatterGather(*this, _input);
+  layers.push_back(op);
+  return op->outputs[0];
+}
+void Model::softmax_cross_entropy(const Tensor& logits, const Tensor& labels, const Tensor& mask) {
+  layers.push_back(new SoftmaxCrossEntropy(*this, logits, labels, mask));
+}
+Tensor Model::indegree_norm(const Tensor& _input) {
+  GnnOp* op = new InDegreeNorm(*this, _input);
+  layers.push_back(op);
+  return op->outputs[0];
+}
+Tensor Model::linear(const Tensor& _input, int outDim, ActiMode activation, Initializer* initializer) {
+  Linear* op = new Linear(*this, _input, outDim, activation, initializer);
+  layers.push_back(op);
+  parameters.push_back(op->weight);   // linear.cc:30
+  return op->outputs[0];
+}
+Tensor Model::relu(const Tensor& _input) {
+  GnnOp* op = new Activation(*this, _input, AC_MODE_RELU);
+  layers.push_back(op);
+  return op->outputs[0];
+}
+Tensor Model::sigmoid(const Tensor& _input) {
+  GnnOp* op = new Activation(*this, _input, AC_MODE_SIGMOID);
+  layers.push_back(op);
+  return op->outputs[0];
+}
+
+void Model::train_mode(void) { mode = MD_MODE_TRAIN; }
+void Model::infer_mode(void) { mode = MD_MODE_INFER; }
+
+namespace {
+struct Wiring {
+  std::map<int, int> producer;    // region -> layer index
+  std::map<int, int> consumers;   // region -> number of consuming op inputs
+  std::map<int, int> consumerOp;  // region -> a consuming layer index
+};
+Wiring wire(const std::vector<GnnOp*>& layers) {
+  Wiring w;
+  for (size_t l = 0; l < layers.size(); l++) {
+    for (int j = 0; j < layers[l]->numOutputs; j++) w.producer[layers[l]->outputs[j].region] = (int)l;
+    for (int j = 0; j < layers[l]->numInputs; j++) {
+      int r = layers[l]->inputs[j].region;
+      if (r < 0) continue;
+      w.consumers[r] += 1;
+      w.consumerOp[r] = (int)l;
+    }
+  }
+  return w;
+}
+template <typename T>
+T* as(GnnOp* op) { return dynamic_cast<T*>(op); }
+}  // namespace
+
+// gnn.cc:625-673.  No graph loading / ResourceManager creation left to do here
+// (Graph's constructor already built the device CSR); what remains is sizing the
+// shared scratch, deciding which tensors need gradients, laying the dW replicas
+// out in one flat buffer and fusing the GCN aggregate block.
+bool Model::init(const Config& config) {
+  (void)config;
+  RuntimeImpl* rt = ctx;
+  myGraph.maxHidden = 0;
+  for (size_t i = 0; i < layers.size(); i++) {
+    for (int j = 0; j < layers[i]->numOutputs; j++)
+      myGraph.maxHidden = std::max(myGraph.maxHidden, (int)layers[i]->outputs[j].dims[0]);
+    for (int j = 0; j < layers[i]->numInputs; j++)
+      if (layers[i]->inputs[j].numDim == 2)
+        myGraph.maxHidden = std::max(myGraph.maxHidden, (int)layers[i]->inputs[j].dims[0]);
+  }
+  // which tensors carry gradients: anything downstream of a parameter
+  for (size_t l = 0; l < layers.size(); l++) {
+    GnnOp* op = layers[l];
+    bool any = false;
+    for (int j = 0; j < op->numInputs; j++)
+      if (op->inputs[j].region >= 0) any = any || rt->t(op->inputs[j].region).requiresGrad;
+    if (as<Linear>(op)) any = true;
+    for (int j = 0; j < op->numOutputs; j++) {
+      rt->t(op->outputs[j].region).requiresGrad = any;
+      rt->t(op->outputs[j].region).produced = true;
+    }
+  }
+  // flat dW buffer (one all-reduce per step instead of the reference's serial
+  // replica sum, optimizer_kernel.cu:88-94)
+  size_t total = 0;
+  for (size_t p = 0; p < parameters.size(); p++) total += (size_t)parameters[p].dims[0] * parameters[p].dims[1];
+  rt->flatGradCount = total;
+  rt->flatGrad = (float*)rt->dmalloc((total ? total : 4) * sizeof(float));
+  ROC_CHECK(cudaMemsetAsync(rt->flatGrad, 0, (total ? total : 4) * sizeof(float), rt->stream));
+  size_t off = 0;
+  for (size_t p = 0; p < parameters.size(); p++) {
+    rt->t(parameters[p].region).grad = rt->flatGrad + off;
+    off += (size_t)parameters[p].dims[0] * parameters[p].dims[1];
+  }
+  // scratch: Linear split-K workspace, SG carry slots, the gathered feature matrix
+  size_t ws = 0;
+  int maxSg = 0;
+  for (size_t l = 0; l < layers.size(); l++) {
+    if (Linear* lin = as<Linear>(layers[l]))
+      ws = std::max(ws, roc_linear_bwd_workspace_bytes(local_rows(), (int)lin->weight.dims[0], (int)lin->weight.dims[1]));
+    if (as<ScatterGather>(layers[l])) maxSg = std::max(maxSg, (int)layers[l]->inputs[0].dims[0]);
+  }
+  rt->ensure_lin_ws(ws);
+  if (maxSg > 0) {
+    ROC_CHECK(roc_sg_plan_reserve(myGraph.plan, maxSg));
+    if (rt->numParts > 1) rt->ensure_gather((size_t)myGraph.numNodes * (size_t)round_up4(maxSg));
+  }
+  // ---- fusion of  linear -> indegree_norm -> scatter_gather -> indegree_norm -> relu  (gnn.cc:81-85)
+  if (fuse) {
+    Wiring w = wire(layers);
+    for (size_t l = 0; l < layers.size(); l++) {
+      ScatterGather* sg = as<ScatterGather>(layers[l]);
+      if (!sg) continue;
+      // upstream: Linear(NONE) -> InDegreeNorm -> SG, each feeding only the next
+      int rin = sg->inputs[0].region;
+      if (w.producer.count(rin) && w.consumers[rin] == 1) {
+        InDegreeNorm* n1 = as<InDegreeNorm>(layers[w.producer[rin]]);
+        if (n1 && n1->fusedInto < 0) {
+          int rl = n1->inputs[0].region;
+          if (w.producer.count(rl) && w.consumers[rl] == 1) {
+            Linear* lin = as<Linear>(layers[w.producer[rl]]);
+            if (lin && lin->activation == AC_MODE_NONE && lin->fwdOut < 0) {
+              lin->flags |= ROC_LINEAR_NORM_EPILOGUE;
+              lin->fwdOut = n1->outputs[0].region;       // linear writes the normalised rows
+              n1->fusedInto = w.producer[rl];
+              sg->bwdEpilogue = ROC_SG_EPI_NORM;          // SG backward writes d(linear out)
+              sg->bwdOut = lin->outputs[0].region;
+            }
+          }
+        }
+      }
+      // downstream: SG -> InDegreeNorm -> [relu]
+      int rout = sg->outputs[0].region;
+      if (w.consumers[rout] == 1) {
+        InDegreeNorm* n2 = as<InDegreeNorm>(layers[w.consumerOp[rout]]);
+        if (n2 && n2->fusedInto < 0) {
+          sg->epilogue = ROC_SG_EPI_NORM;
+          sg->fwdOut = n2->outputs[0].region;
+          n2->fusedInto = (int)l;   // forward only; its backward kernel still runs
+          int rn = n2->outputs[0].region;
+          if (w.consumers[rn] == 1) {
+            Activation* act = as<Activation>(layers[w.consumerOp[rn]]);
+            if (act && act->actiMode == AC_MODE_RELU && act->fusedInto < 0) {
+              sg->epilogue |= ROC_SG_EPI_RELU;
+              sg->fwdOut = act->outputs[0].region;
+              act->fusedInto = (int)l;
+              n2->reluMaskOf = act->outputs[0].region;   // backward: relu mask + norm in one pass
+              n2->bwdIn = act->outputs[0].region;
+            }
+          }
+        }
+      }
+    }
+  }
+  for (size_t l = 0; l < layers.size(); l++) layers[l]->init(*this);
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  return true;
+}
+
+// gnn.cc:696-700
+void Model::forward(void) {
+  if (mode == MD_MODE_TRAIN) ctx->trainStep += 1;
+  for (size_t l = 0; l < layers.size(); l++) layers[l]->forward(*this);
+}
+
+// gnn.cc:702-716
+void Model::backward(void) {
+  std::set<int> resetedInputGrads;
+  for (int l = (int)layers.size() - 1; l >= 0; l--) {
+    for (int i = 0; i < layers[l]->numInputs; i++) {
+      int r = layers[l]->inputs[i].region;
+      if (resetedInputGrads.find(r) == resetedInputGrads.end()) {
+        resetedInputGrads.insert(r);
+        layers[l]->resetInputGrads[i] = true;
+      } else {
+        // This input's gradients has been reseted by other layers
+        layers[l]->resetInputGrads[i] = false;
+      }
+    }
+    layers[l]->backward(*this);
+  }
+}
+
+// gnn.cc:718-724 (+ the replica sum of optimizer_kernel.cu:88-94 as one all-reduce)
+void Model::update(void) {
+  RuntimeImpl* rt = ctx;
+  optimizer->next();
+  if (rt->numParts > 1 && rt->flatGradCount) {
+    ROC_ASSERT(rt->commReady);
+    ROC_CHECK(rt->comm.allreduce_sum(rt->flatGrad, rt->flatGradCount, rt->stream));
+  }
+  for (int p = (int)parameters.size() - 1; p >= 0; p--) optimizer->update(&parameters[p]);
+}
+
+// gnn.cc:726-739
+void Model::zero_gradients(void) {
+  RuntimeImpl* rt = ctx;
+  if (rt->flatGradCount)
+    ROC_CHECK(cudaMemsetAsync(rt->flatGrad, 0, rt->flatGradCount * sizeof(float), rt->stream));
+}
+
+void Model::set_tensor(const Tensor& t, const void* host, bool grad) {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(t.region);
+  float* dst = grad ? rt->grad(t.region) : rt->data(t.region);
+  ROC_CHECK(cudaMemcpy2DAsync(dst, (size_t)x.ld * 4, host, (size_t)x.H * 4, (size_t)x.H * 4, (size_t)x.rows,
+                              cudaMemcpyHostToDevice, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+}
+
+void Model::get_tensor(const Tensor& t, void* host, bool grad) const {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(t.region);
+  const float* src = grad ? rt->grad(t.region) : rt->data(t.region);
+  ROC_CHECK(cudaMemcpy2DAsync(host, (size_t)x.H * 4, src, (size_t)x.ld * 4, (size_t)x.H * 4, (size_t)x.rows,
+                              cudaMemcpyDeviceToHost, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+}
+
+void Model::set_labels(const Tensor& label, const int* host_class_idx) {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(label.region);
+  if (!x.labelIdx) x.labelIdx = (int32_t*)rt->dmalloc((size_t)x.rows * sizeof(int32_t));
+  for (int64_t v = 0; v < x.rows; v++) ROC_ASSERT(host_class_idx[v] >= 0 && host_class_idx[v] < x.H);  // load_task.cu:120
+  ROC_CHECK(cudaMemcpyAsync(x.labelIdx, host_class_idx, (size_t)x.rows * sizeof(int32_t), cudaMemcpyHostToDevice, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+}
+
+roc_perf_metrics Model::last_metrics(void) const {
+  RuntimeImpl* rt = ctx;
+  ROC_CHECK(cudaMemcpyAsync(&rt->h_perf, rt->d_perf, sizeof(roc_perf_metrics), cudaMemcpyDeviceToHost, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  return rt->h_perf;
+}
+
+// ---- dataset loaders: load_task.cu:25-199 (formats in SURVEY Appendix C) ----
+void Model::load_features(const Tensor& input, const std::string& prefix) {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(input.region);
+  const int inDim = x.H;
+  const size_t nloc = (size_t)x.rows;
+  std::vector<float> buf(nloc * (size_t)inDim);
+  std::string binFile = prefix + ".feats.bin", csvFile = prefix + ".feats.csv";
+  FILE* binFin = fopen(binFile.c_str(), "rb");
+  if (binFin == NULL) {
+    // CSV: one line per vertex, inDim comma-separated values (load_task.cu:42-62); the
+    // whole file is parsed so the .feats.bin cache can be written (load_task.cu:63-65)
+    fprintf(stderr, "[roc_b200] Load features from CSV: %s\n", csvFile.c_str());
+    std::ifstream csvFin(csvFile.c_str());
+    if (!csvFin.good()) ROC_FATAL(("cannot open " + binFile + " or " + csvFile).c_str());
+    std::vector<float> all((size_t)myGraph.numNodes * inDim);
+    std::string line, word;
+    for (V_ID v = 0; v < myGraph.numNodes; v++) {
+      std::getline(csvFin, line);
+      std::stringstream ss(line);
+      int feat_cnt = 0;
+      while (std::getline(ss, word, ',')) {
+        ROC_ASSERT(feat_cnt < inDim);
+        all[(size_t)v * inDim + feat_cnt] = std::stof(word);
+        feat_cnt++;
+      }
+      ROC_ASSERT(feat_cnt == inDim);
+    }
+    if (rt->myPart == 0) {
+      FILE* binFout = fopen(binFile.c_str(), "wb");
+      if (binFout) { fwrite(all.data(), sizeof(float), all.size(), binFout); fclose(binFout); }
+    }
+    memcpy(buf.data(), all.data() + (size_t)myGraph.rowLeft * inDim, buf.size() * sizeof(float));
+  } else {
+    ROC_ASSERT(fseeko(binFin, (off_t)((size_t)myGraph.rowLeft * inDim * sizeof(float)), SEEK_SET) == 0);
+    size_t ret = fread(buf.data(), sizeof(float), buf.size(), binFin);
+    ROC_ASSERT(ret == buf.size());
+    fclose(binFin);
+  }
+  set_tensor(input, buf.data());
+}
+
+void Model::load_labels(const Tensor& label, const std::string& prefix) {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(label.region);
+  std::string filename = prefix + ".label";
+  FILE* file = fopen(filename.c_str(), "r");
+  if (!file) ROC_FATAL(("cannot open " + filename).c_str());
+  int idx;
+  for (V_ID v = 0; v < myGraph.rowLeft; v++) ROC_ASSERT(fscanf(file, "%d", &idx) == 1);
+  std::vector<int> cls((size_t)x.rows);
+  for (int64_t v = 0; v < x.rows; v++) {
+    ROC_ASSERT(fscanf(file, "%d", &idx) == 1);
+    cls[(size_t)v] = idx;
+  }
+  fclose(file);
+  set_labels(label, cls.data());
+}
+
+void Model::load_train_mask(const Tensor& mask, const std::string& prefix) {
+  RuntimeImpl* rt = ctx;
+  TensorImpl& x = rt->t(mask.region);
+  std::string filename = prefix + ".mask";
+  std::ifstream fin(filename.c_str());
+  if (!fin.good()) ROC_FATAL(("cannot open " + filename).c_str());
+  std::string line;
+  for (V_ID v = 0; v < myGraph.rowLeft; v++) std::getline(fin, line);
+  std::vector<int> m((size_t)x.rows);
+  for (int64_t v = 0; v < x.rows; v++) {
+    std::getline(fin, line);
+    if (line == "Train") m[(size_t)v] = MASK_TRAIN;
+    else if (line == "Val") m[(size_t)v] = MASK_VAL;
+    else if (line == "Test") m[(size_t)v] = MASK_TEST;
+    else if (line == "None") m[(size_t)v] = MASK_NONE;
+    else { printf("Unrecognized mask: %s\n", line.c_str()); ROC_ASSERT(false); }
+  }
+  set_tensor(mask, m.data());
+}
+
+// -------------------------------------------------------- ScatterGather -----
+ScatterGather::ScatterGather(const Model& model, const Tensor& _input)
+    : GnnOp(_input), epilogue(0), bwdEpilogue(0), fwdOut(-1), bwdOut(-1) {
+  // scattergather.cc:33-37
+  ROC_ASSERT(inputs[0].type == Tensor::NODE_TENSOR);
+  ROC_ASSERT(inputs[0].numDim == 2);
+  ROC_ASSERT(inputs[0].dims[1] == model.myGraph.numNodes);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>((int)inputs[0].dims[0]);
+}
+void ScatterGather::init(const Model&) {}
+
+namespace {
+// The exchange step of ScatterGather (scattergather.cc:69-73 asks Legion for the
+// WHOLE input region): all-gather every partition's slab into [numNodes][ld] so
+// the kernel can index rows by global source id.  numParts == 1: no copy at all.
+const float* gathered(const Model& model, const float* local, int64_t ld) {
+  RuntimeImpl* rt = model.ctx;
+  if (rt->numParts == 1) return local;
+  ROC_ASSERT(rt->commReady);
+  const Graph& g = model.myGraph;
+  rt->ensure_gather((size_t)g.numNodes * (size_t)ld);
+  std::vector<size_t> counts((size_t)rt->numParts), offs((size_t)rt->numParts);
+  for (int r = 0; r < rt->numParts; r++) {
+    counts[(size_t)r] = ((size_t)g.vbounds[2 * r + 1] - g.vbounds[2 * r] + 1) * (size_t)ld;
+    offs[(size_t)r] = (size_t)g.vbounds[2 * r] * (size_t)ld;
+  }
+  ROC_CHECK(rt->comm.allgatherv(local, rt->gatherBuf, counts, offs, rt->stream));
+  return rt->gatherBuf;
+}
+}  // namespace
+
+void ScatterGather::forward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  const int H = (int)inputs[0].dims[0];
+  const int64_t ldIn = rt->t(inputs[0].region).ld;
+  const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
+  const float* src = gathered(model, rt->data(inputs[0].region), ldIn);
+  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, rt->data(outRegion), rt->t(outRegion).ld,
+                                   epilogue, rt->stream));
+}
+
+void ScatterGather::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  ROC_ASSERT(resetInputGrads[0]);   // scattergather_kernel.cu:167
+  if (!rt->t(inputs[0].region).requiresGrad) return;
+  const int H = (int)inputs[0].dims[0];
+  const int64_t ld = rt->t(outputs[0].region).ld;
+  const int dstRegion = bwdOut >= 0 ? bwdOut : inputs[0].region;
+  // Forward and backward do exactly the same thing, on gradients (scattergather_kernel.cu:168-169)
+  const float* src = gathered(model, rt->grad(outputs[0].region), ld);
+  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, rt->grad(dstRegion), rt->t(dstRegion).ld,
+                                   bwdEpilogue, rt->stream));
+}
+
+// --------------------------------------------------------- InDegreeNorm -----
+InDegreeNorm::InDegreeNorm(const Model& model, const Tensor& _input) : GnnOp(_input), reluMaskOf(-1), bwdIn(-1) {
+  ROC_ASSERT(inputs[0].type == Tensor::NODE_TENSOR);   // graphnorm.cc:33-35
+  ROC_ASSERT(inputs[0].numDim == 2);
+  ROC_ASSERT(inputs[0].dims[1] == model.myGraph.numNodes);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>((int)inputs[0].dims[0]);
+}
+void InDegreeNorm::init(const Model&) {}
+
+void InDegreeNorm::forward(const Model& model) {
+  if (fusedInto >= 0) return;   // done in the producer's epilogue
+  RuntimeImpl* rt = model.ctx;
+  const Graph& g = model.myGraph;
+  ROC_CHECK(roc_indegree_norm(g.rowLeft, g.rowRight, g.colLeft, (int)inputs[0].dims[0], g.d_rowEnd,
+                              rt->data(inputs[0].region), rt->t(inputs[0].region).ld, rt->data(outputs[0].region),
+                              rt->t(outputs[0].region).ld, NULL, rt->stream));
+}
+
+void InDegreeNorm::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  ROC_ASSERT(resetInputGrads[0]);   // graphnorm_kernel.cu:133
+  if (!rt->t(inputs[0].region).requiresGrad) return;
+  // fused into the linear's epilogue forward => the SG backward epilogue already
+  // produced d(linear out); nothing to do here
+  if (fusedInto >= 0 && dynamic_cast<Linear*>(model.layers[(size_t)fusedInto])) return;
+  const Graph& g = model.myGraph;
+  const int src = bwdIn >= 0 ? bwdIn : outputs[0].region;
+  ROC_CHECK(roc_indegree_norm(g.rowLeft, g.rowRight, g.colLeft, (int)inputs[0].dims[0], g.d_rowEnd, rt->grad(src),
+                              rt->t(src).ld, rt->grad(inputs[0].region), rt->t(inputs[0].region).ld,
+                              reluMaskOf >= 0 ? rt->data(reluMaskOf) : NULL, rt->stream));
+}
+
+// ----------------------------------------------------------------- Linear ---
+Linear::Linear(const Model& model, const Tensor& _input, int outDim, ActiMode _activation, Initializer* initializer)
+    : GnnOp(_input), activation(_activation), flags(0), fwdOut(-1), bwdIn(-1) {
+  ROC_ASSERT(_input.numDim == 2);   // linear.cc:41-42
+  ROC_ASSERT(_input.dims[1] == model.myGraph.numNodes);
+  weight = model.create_weight_tensor((int)_input.dims[0], outDim, initializer);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>(outDim);
+}
+void Linear::init(const Model&) {}
+
+void Linear::forward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  const Graph& g = model.myGraph;
+  const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
+  ROC_CHECK(roc_linear_fwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
+                           rt->t(inputs[0].region).ld, rt->data(weight.region), rt->data(outRegion),
+                           rt->t(outRegion).ld, (int)activation, flags, g.d_rowEnd, g.colLeft, rt->stream));
+}
+
+void Linear::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  const int gy = bwdIn >= 0 ? bwdIn : outputs[0].region;
+  float* dX = rt->t(inputs[0].region).requiresGrad ? rt->grad(inputs[0].region) : NULL;   // Q8: leaf grads skipped
+  const float* Y = (activation != AC_MODE_NONE) ? rt->data(outputs[0].region) : NULL;
+  ROC_CHECK(roc_linear_bwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
+                           rt->t(inputs[0].region).ld, rt->data(weight.region), Y, rt->t(outputs[0].region).ld,
+                           rt->grad(gy), rt->t(gy).ld, rt->grad(weight.region), dX, rt->t(inputs[0].region).ld,
+                           (int)activation, resetInputGrads[0] ? 0 : 1, rt->linWs, rt->linWsBytes, rt->stream));
+}
+
+// ------------------------------------------------------------- Activation ---
+Activation::Activation(const Model& model, const Tensor& _input, ActiMode _actiMode)
+    : GnnOp(_input), actiMode(_actiMode) {
+  ROC_ASSERT(_input.numDim == 2);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>((int)_input.dims[0]);
+}
+void Activation::init(const Model&) {}
+void Activation::forward(const Model& model) {
+  if (fusedInto >= 0) return;
+  RuntimeImpl* rt = model.ctx;
+  ROC_CHECK(roc_activation_fwd(model.local_rows(), (int)inputs[0].dims[0], (int)actiMode, rt->data(inputs[0].region),
+                               rt->t(inputs[0].region).ld, rt->data(outputs[0].region), rt->t(outputs[0].region).ld,
+                               rt->stream));
+}
+void Activation::backward(const Model& model) {
+  if (fusedInto >= 0) return;   // mask applied by the fused indegree_norm backward
+  RuntimeImpl* rt = model.ctx;
+  if (!rt->t(inputs[0].region).requiresGrad) return;
+  ROC_CHECK(roc_activation_bwd(model.local_rows(), (int)inputs[0].dims[0], (int)actiMode, rt->data(outputs[0].region),
+                               rt->t(outputs[0].region).ld, rt->grad(outputs[0].region), rt->t(outputs[0].region).ld,
+                               rt->grad(inputs[0].region), rt->t(inputs[0].region).ld, resetInputGrads[0] ? 0 : 1,
+                               rt->stream));
+}
+
+// ---------------------------------------------------------------- Element ---
+Element::Element(const Model& model, const Tensor& input0, const Tensor& input1, ElementType _elementType)
+    : GnnOp(input0, input1), elementType(_elementType) {
+  ROC_ASSERT(input0.numDim == input1.numDim);   // element.cc:33-36
+  for (int i = 0; i < input0.numDim; i++) ROC_ASSERT(input0.dims[i] == input1.dims[i]);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>((int)input0.dims[0]);
+}
+void Element::init(const Model&) {}
+void Element::forward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  ROC_ASSERT(elementType == EW_TYPE_ADD);
+  ROC_CHECK(roc_add_fwd(model.local_rows(), (int)inputs[0].dims[0], rt->data(inputs[0].region),
+                        rt->t(inputs[0].region).ld, rt->data(inputs[1].region), rt->t(inputs[1].region).ld,
+                        rt->data(outputs[0].region), rt->t(outputs[0].region).ld, rt->stream));
+}
+void Element::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  ROC_ASSERT(elementType == EW_TYPE_ADD);   // element_kernel.cu:102-104
+  float* dA = rt->t(inputs[0].region).requiresGrad ? rt->grad(inputs[0].region) : NULL;
+  float* dB = rt->t(inputs[1].region).requiresGrad ? rt->grad(inputs[1].region) : NULL;
+  ROC_CHECK(roc_add_bwd(model.local_rows(), (int)inputs[0].dims[0], rt->grad(outputs[0].region),
+                        rt->t(outputs[0].region).ld, dA, rt->t(inputs[0].region).ld, resetInputGrads[0] ? 0 : 1, dB,
+                        rt->t(inputs[1].region).ld, resetInputGrads[1] ? 0 : 1, rt->stream));
+}
+
+// ---------------------------------------------------------------- Dropout ---
+Dropout::Dropout(const Model& model, const Tensor& _input, float _rate, int _seed)
+    : GnnOp(_input), rate(_rate), seed(_seed), opIndex(0) {
+  ROC_ASSERT(_input.numDim == 2);
+  ROC_ASSERT(_input.type == Tensor::NODE_TENSOR);
+  numOutputs = 1;
+  outputs[0] = model.create_node_tensor<DATATYPE>((int)_input.dims[0]);
+}
+void Dropout::init(const Model&) {}
+void Dropout::forward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  // train: masked scale (dropout_kernel.cu:98-99); infer: plain copy (:159-180)
+  const float r = (model.mode == MD_MODE_TRAIN) ? rate : 0.0f;
+  const uint64_t key = ((uint64_t)(uint32_t)seed << 32) | (uint32_t)opIndex;
+  ROC_CHECK(roc_dropout_fwd(model.local_rows(), (int)inputs[0].dims[0], model.myGraph.rowLeft, r, key, rt->trainStep,
+                            rt->data(inputs[0].region), rt->t(inputs[0].region).ld, rt->data(outputs[0].region),
+                            rt->t(outputs[0].region).ld, rt->stream));
+}
+void Dropout::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  if (!rt->t(inputs[0].region).requiresGrad) return;   // leaf input (Q8)
+  ROC_ASSERT(resetInputGrads[0]);   // dropout_kernel.cu:119
+  const float r = (model.mode == MD_MODE_TRAIN) ? rate : 0.0f;
+  const uint64_t key = ((uint64_t)(uint32_t)seed << 32) | (uint32_t)opIndex;
+  ROC_CHECK(roc_dropout_bwd(model.local_rows(), (int)inputs[0].dims[0], model.myGraph.rowLeft, r, key, rt->trainStep,
+                            rt->grad(outputs[0].region), rt->t(outputs[0].region).ld, rt->grad(inputs[0].region),
+                            rt->t(inputs[0].region).ld, rt->stream));
+}
+
+// ---------------------------------------------------- SoftmaxCrossEntropy ---
+SoftmaxCrossEntropy::SoftmaxCrossEntropy(const Model&, const Tensor& _logit, const Tensor& _label, const Tensor& _mask)
+    : GnnOp(_logit, _label, _mask), epoch_num(0) {
+  ROC_ASSERT(_logit.numDim == 2);   // softmax.cc:36-39
+  ROC_ASSERT(_label.numDim == 2);
+  ROC_ASSERT(_label.dims[0] == _logit.dims[0]);
+  ROC_ASSERT(_label.dims[1] == _logit.dims[1]);
+  numOutputs = 0;
+}
+void SoftmaxCrossEntropy::init(const Model&) {}
+void SoftmaxCrossEntropy::forward(const Model& model) {
+  mode = model.mode;
+  if (model.mode == MD_MODE_TRAIN) {
+    // Do nothing in training forward (softmax.cc:48-49)
+  } else {
+    backward(model);   // softmax.cc:50-54: inference reuses the backward task for metrics
+  }
+}
+void SoftmaxCrossEntropy::backward(const Model& model) {
+  RuntimeImpl* rt = model.ctx;
+  mode = model.mode;
+  if (mode == MD_MODE_TRAIN) epoch_num++;
+  ROC_ASSERT(inputs[2].region >= 0);   // softmax_kernel.cu:157-160: masks are required
+  const int C = (int)inputs[0].dims[0];
+  TensorImpl& lab = rt->t(inputs[1].region);
+  ROC_CHECK(cudaMemsetAsync(rt->d_perf, 0, sizeof(roc_perf_metrics), rt->stream));
+  const int32_t* mask = reinterpret_cast<const int32_t*>(rt->data(inputs[2].region));
+  if (lab.labelIdx) {
+    ROC_CHECK(roc_softmax_xent_bwd_idx(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
+                                       lab.labelIdx, mask, rt->grad(inputs[0].region), rt->t(inputs[0].region).ld,
+                                       rt->d_perf, rt->stream));
+  } else {
+    ROC_CHECK(roc_softmax_xent_bwd(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
+                                   rt->data(inputs[1].region), lab.ld, mask, rt->grad(inputs[0].region),
+                                   rt->t(inputs[0].region).ld, rt->d_perf, rt->stream));
+  }
+  if (mode == MD_MODE_INFER && model.printMetrics) {
+    roc_perf_metrics p = model.last_metrics();
+    // softmax_kernel.cu:141-152 (printed once per partition, quirk Q20)
+    fprintf(stderr,
+            "\t[INFER][%d] train_loss: %.4lf  train_accuracy: %.2lf%%(%d/%d)  val_accuracy: %.2lf%%(%d/%d)  "
+            "test_accuracy: %.2lf%%(%d/%d)\n",
+            epoch_num, p.trainLoss, p.trainCorrect * 100.0f / p.trainAll, p.trainCorrect, p.trainAll,
+            p.valCorrect * 100.0f / p.valAll, p.valCorrect, p.valAll, p.testCorrect * 100.0f / p.testAll,
+            p.testCorrect, p.testAll);
+  }
+}
+
+// ----------------------------------------------------------- initializers ---
+// initializer.cc:31-46 + initializer_kernel.cu:22-51: cuRAND's default XORWOW
+// generator seeded with the next std::rand(), uniform (0,1] over the weight's
+// linear memory order, then W = 2*s*u - s.  cuRAND is called at init only, so
+// the weights match the reference bit for bit for a given -seed.
+void GlorotUniform::init(const Model* model, const Tensor* p) {
+  RuntimeImpl* rt = model->ctx;
+  ROC_ASSERT(p->numDim == 2);
+  int num = std::rand();
+  const int inputDim = (int)p->dims[0], outputDim = (int)p->dims[1];
+  const size_t vol = (size_t)inputDim * outputDim;
+  float scale = sqrt(6.0 / (inputDim + outputDim));
+  curandGenerator_t gen;
+  ROC_CHECK(curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT));
+  ROC_CHECK(curandSetStream(gen, rt->stream));
+  ROC_CHECK(curandSetPseudoRandomGeneratorSeed(gen, (unsigned long long)num));
+  float* w = rt->data(p->region);
+  ROC_CHECK(curandGenerateUniform(gen, w, vol));
+  ROC_CHECK(roc_scale((int64_t)vol, -scale, scale, w, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  curandDestroyGenerator(gen);
+}
+
+void ZerosInitializer::init(const Model* model, const Tensor* p) {
+  RuntimeImpl* rt = model->ctx;
+  ROC_ASSERT(p->numDim == 2);
+  TensorImpl& x = rt->t(p->region);
+  ROC_CHECK(roc_fill(x.rows, x.H, 0.0f, rt->data(p->region), x.ld, rt->stream));
+}
+
+// -------------------------------------------------------------- optimizer ---
+// optimizer.cc:22-70: m and v per parameter, zero-initialised; must be built
+// after every linear() call (it walks model->parameters).
+AdamOptimizer::AdamOptimizer(const Model* _model, double _alpha, double _beta1, double _beta2, double _weight_decay,
+                             double _epsilon)
+    : Optimizer(_model), alpha(_alpha), beta1(_beta1), beta2(_beta2), weight_decay(_weight_decay),
+      epsilon(_epsilon), alpha_t(_alpha), beta1_t(1.0f), beta2_t(1.0f) {
+  RuntimeImpl* rt = _model->ctx;
+  ZerosInitializer zeros;
+  for (size_t i = 0; i < model->parameters.size(); i++) {
+    const Tensor& p = model->parameters[i];
+    Tensor t = p;
+    t.region = rt->new_tensor((int64_t)p.dims[1], (int)p.dims[0], (int64_t)p.dims[0], false, true);
+    v_regions[p.region] = t.region;
+    zeros.init(_model, &t);
+    t.region = rt->new_tensor((int64_t)p.dims[1], (int)p.dims[0], (int64_t)p.dims[0], false, true);
+    m_regions[p.region] = t.region;
+    zeros.init(_model, &t);
+  }
+}
+
+void AdamOptimizer::set_weight_decay(double _weight_decay) { weight_decay = _weight_decay; }
+
+// optimizer.cc:79-85
+void AdamOptimizer::next(void) {
+  beta1_t *= beta1;
+  beta2_t *= beta2;
+  alpha_t = alpha * sqrt(1 - beta2_t) / (1 - beta1_t);
+}
+
+// optimizer.cc:87-119 + optimizer_kernel.cu:66-103 (the gradient was already summed
+// over partitions by Model::update's all-reduce)
+void AdamOptimizer::update(const Tensor* p) {
+  RuntimeImpl* rt = model->ctx;
+  ROC_ASSERT(v_regions.find(p->region) != v_regions.end());
+  ROC_ASSERT(m_regions.find(p->region) != m_regions.end());
+  const int64_t count = (int64_t)p->dims[0] * (int64_t)p->dims[1];
+  ROC_CHECK(roc_adam_update(count, (float)alpha_t, (float)beta1, (float)beta2, (float)weight_decay, (float)epsilon,
+                            rt->grad(p->region), rt->data(m_regions[p->region]), rt->data(v_regions[p->region]),
+                            rt->data(p->region), rt->stream));
+}
+
+// ------------------------------------------------------------------- CLI ----
+// Same flags as gnn.cc:114-179, including "-dr" being taken by dropout before
+// decay-rate can see it (quirk Q19).
+void parse_input_args(char** argv, int argc, Config& config) {
+  for (int i = 1; i < argc; i++) {
+    const std::string a(argv[i]);
+    const bool more = i + 1 < argc;
+    if (a == "-seed" && more) config.seed = atoi(argv[++i]);
+    else if ((a == "-ng" || a == "-ll:gpu") && more) config.numGPUs = atoi(argv[++i]);
+    else if ((a == "-e" || a == "-epoch") && more) config.numEpochs = atoi(argv[++i]);
+    else if (a == "-lr" && more) config.learning_rate = atof(argv[++i]);
+    else if ((a == "-dropout" || a == "-dr") && more) config.dropout_rate = atof(argv[++i]);
+    else if ((a == "-decay" || a == "-wd") && more) config.weight_decay = atof(argv[++i]);
+    else if (a == "-decay-rate" && more) config.decay_rate = atof(argv[++i]);
+    else if ((a == "-decay-step" || a == "-ds") && more) config.decay_steps = atoi(argv[++i]);
+    else if (a == "-file" && more) config.filename = std::string(argv[++i]);
+    else if (a == "-verbose" || a == "-v") config.verbose = true;
+    else if (a == "-layers" && more) {
+      std::stringstream ss((std::string(argv[++i])));
+      std::string word;
+      config.layers.clear();
+      while (std::getline(ss, word, '-')) config.layers.push_back(std::stoi(word));
+    }
+  }
+}

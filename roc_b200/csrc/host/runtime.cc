@@ -1,0 +1,210 @@
+// runtime.cc — Runtime: the process's GPU, stream, device memory and NCCL communicator.
+// Replaces what Legion/Realm + GnnMapper + ResourceManager provided to the reference
+// (gnn_mapper.cc, resourcemanager.cc, load_task.cu:296-376): here it is one
+// cudaSetDevice, one stream and plain device allocations that live as long as the Runtime.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstring>
+
+#include "host_internal.h"
+
+namespace roc {
+namespace host {
+
+void fatal(const char* what, const char* file, int line) {
+  fprintf(stderr, "%s\n%s:%d\nAborting...\n", what, file, line);
+  fflush(stderr);
+  exit(1);
+}
+
+void* RuntimeImpl::dmalloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    char b[160];
+    snprintf(b, sizeof(b), "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    ROC_FATAL(b);
+  }
+  allocs.push_back(p);
+  return p;
+}
+
+void RuntimeImpl::dfree_all() {
+  for (void* p : allocs) cudaFree(p);
+  allocs.clear();
+}
+
+int RuntimeImpl::new_tensor(int64_t rows, int H, int64_t ld, bool isInt, bool isWeight) {
+  TensorImpl ti;
+  ti.rows = rows; ti.H = H; ti.ld = ld; ti.isInt = isInt; ti.isWeight = isWeight;
+  tensors.push_back(ti);
+  return (int)tensors.size() - 1;
+}
+
+float* RuntimeImpl::data(int region) {
+  TensorImpl& x = t(region);
+  if (!x.data) {
+    size_t bytes = (size_t)x.rows * (size_t)x.ld * sizeof(float);
+    x.data = (float*)dmalloc(bytes);
+    ROC_CHECK(cudaMemsetAsync(x.data, 0, bytes ? bytes : 16, stream));
+  }
+  return x.data;
+}
+
+float* RuntimeImpl::grad(int region) {
+  TensorImpl& x = t(region);
+  if (!x.grad) {
+    size_t bytes = (size_t)x.rows * (size_t)x.ld * sizeof(float);
+    x.grad = (float*)dmalloc(bytes);
+    ROC_CHECK(cudaMemsetAsync(x.grad, 0, bytes ? bytes : 16, stream));
+  }
+  return x.grad;
+}
+
+void RuntimeImpl::ensure_gather(size_t floats) {
+  if (floats <= gatherFloats) return;
+  gatherBuf = (float*)dmalloc(floats * sizeof(float));   // old one stays in the arena (freed at exit)
+  gatherFloats = floats;
+}
+
+void RuntimeImpl::ensure_lin_ws(size_t bytes) {
+  if (bytes <= linWsBytes) return;
+  linWs = dmalloc(bytes);
+  linWsBytes = bytes;
+}
+
+// ------------------------------------------------------------------- NCCL ---
+namespace {
+struct NcclFns {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+};
+NcclFns g_nccl;
+void* g_ncclLib = nullptr;
+
+bool load_nccl() {
+  if (g_ncclLib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // prefer one already in the process (torch's)
+    if (h) break;
+  }
+  if (!h)
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) { fprintf(stderr, "roc_b200: cannot load libnccl: %s\n", dlerror()); return false; }
+#define SYM(field, name) \
+  *(void**)(&g_nccl.field) = dlsym(h, name); \
+  if (!g_nccl.field) { fprintf(stderr, "roc_b200: libnccl lacks %s\n", name); return false; }
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(Broadcast, "ncclBroadcast");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_ncclLib = h;
+  return true;
+}
+}  // namespace
+
+bool Comm::load() { return load_nccl(); }
+
+bool Comm::unique_id(unsigned char id[128]) {
+  if (!load_nccl()) return false;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  if (g_nccl.GetUniqueId(&u) != ncclSuccess) return false;
+  memcpy(id, &u, 128);
+  return true;
+}
+
+bool Comm::init(int r, int w, const unsigned char id[128]) {
+  if (!load_nccl()) return false;
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t c;
+  ncclResult_t rc = g_nccl.CommInitRank(&c, w, u, r);
+  if (rc != ncclSuccess) {
+    fprintf(stderr, "roc_b200: ncclCommInitRank: %s\n", g_nccl.GetErrorString(rc));
+    return false;
+  }
+  comm = c; rank = r; world = w;
+  return true;
+}
+
+int Comm::allgatherv(const float* sendbuf, float* recvbuf, const std::vector<size_t>& counts,
+                     const std::vector<size_t>& offsets, cudaStream_t st) {
+  // NCCL has no all-gather-v: one grouped broadcast per owner, landing each slab at
+  // its row offset of the gathered matrix.
+  ncclComm_t c = (ncclComm_t)comm;
+  if (g_nccl.GroupStart() != ncclSuccess) return -1;
+  for (int r = 0; r < world; r++) {
+    if (counts[r] == 0) continue;
+    ncclResult_t rc = g_nccl.Broadcast(r == rank ? (const void*)sendbuf : (const void*)(recvbuf + offsets[r]),
+                                       recvbuf + offsets[r], counts[r], ncclFloat, r, c, st);
+    if (rc != ncclSuccess) { g_nccl.GroupEnd(); return -2; }
+  }
+  return g_nccl.GroupEnd() == ncclSuccess ? 0 : -3;
+}
+
+int Comm::allreduce_sum(float* buf, size_t count, cudaStream_t st) {
+  return g_nccl.AllReduce(buf, buf, count, ncclFloat, ncclSum, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
+}
+
+int Comm::allreduce_sum_i32(int* buf, size_t count, cudaStream_t st) {
+  return g_nccl.AllReduce(buf, buf, count, ncclInt32, ncclSum, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
+}
+
+void Comm::destroy() {
+  if (comm && g_ncclLib) g_nccl.CommDestroy((ncclComm_t)comm);
+  comm = nullptr;
+}
+
+}  // namespace host
+}  // namespace roc
+
+using namespace roc::host;
+
+Runtime::Runtime(int device, int myPart, int numParts) {
+  impl = new RuntimeImpl();
+  impl->device = device; impl->myPart = myPart; impl->numParts = numParts;
+  if (numParts < 1 || myPart < 0 || myPart >= numParts || numParts > MAX_NUM_PARTS)
+    ROC_FATAL("Runtime: bad partition index / count");
+  if (roc_device_count() <= 0)
+    ROC_FATAL("roc_b200: no CUDA device visible - this engine has no CPU fallback");
+  ROC_CHECK(cudaSetDevice(device));
+  ROC_CHECK(cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking));
+  impl->d_perf = (roc_perf_metrics*)impl->dmalloc(sizeof(roc_perf_metrics));
+  ROC_CHECK(cudaMemsetAsync(impl->d_perf, 0, sizeof(roc_perf_metrics), impl->stream));
+}
+
+Runtime::~Runtime() {
+  if (!impl) return;
+  cudaSetDevice(impl->device);
+  cudaDeviceSynchronize();
+  impl->comm.destroy();
+  impl->dfree_all();
+  if (impl->stream) cudaStreamDestroy(impl->stream);
+  delete impl;
+}
+
+bool Runtime::nccl_unique_id(unsigned char id[128]) { return Comm::unique_id(id); }
+
+bool Runtime::init_nccl(const unsigned char id[128]) {
+  ROC_CHECK(cudaSetDevice(impl->device));
+  if (impl->numParts == 1) return true;
+  impl->commReady = impl->comm.init(impl->myPart, impl->numParts, id);
+  return impl->commReady;
+}
+
+void Runtime::synchronize() { ROC_CHECK(cudaStreamSynchronize(impl->stream)); }

@@ -1,0 +1,85 @@
+// linear.cu — C-ABI entry points of the Linear op and the kernel dispatcher.
+// Replaces Linear::forward_task / backward_task (linear_kernel.cu:19-118, 129-245).
+#include <cstdlib>
+#include "common.cuh"
+
+namespace roc {
+int simt_dw_splits(int64_t rows, int inDim, int outDim);
+int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
+                    int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
+int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
+                   int64_t ldDX, int accumulate, cudaStream_t st);
+int simt_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
+                   float* dW, float* workspace, size_t wsBytes, cudaStream_t st);
+int relu_bwd_inplace(int64_t rows, int H, const float* Y, int64_t ldY, float* dY, int64_t ldDY, cudaStream_t st);
+
+// tensor-core path (linear_tc.cu); each returns ROC_ERR_UNSUPPORTED when the
+// shape / alignment is outside what the tcgen05 kernels take.
+int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
+                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
+size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim);
+int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
+                 float* dW, float* workspace, size_t wsBytes, cudaStream_t st);
+
+// ROC_B200_GEMM=simt forces the exact-fp32 SIMT kernels (used by tests to
+// cross-check the tensor-core path).
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ROC_B200_GEMM"); v = (e && e[0] == 's') ? 1 : 0; }
+  return v == 1;
+}
+}  // namespace roc
+
+using namespace roc;
+
+extern "C" int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                              float* Y, int64_t ldY, int activation, int flags, const roc_eid_t* rowEnd,
+                              roc_eid_t colLeft, roc_stream_t stream) {
+  if (!X || !W || !Y || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldY < outDim) return ROC_ERR_INVALID;
+  if (activation != ROC_AC_MODE_NONE && activation != ROC_AC_MODE_RELU) return ROC_ERR_UNSUPPORTED;  // linear_kernel.cu:96
+  if ((flags & ROC_LINEAR_NORM_EPILOGUE) && !rowEnd) return ROC_ERR_INVALID;
+  if (rows == 0) return ROC_OK;
+  const uint64_t* re = (flags & ROC_LINEAR_NORM_EPILOGUE) ? rowEnd : nullptr;
+  const int relu = activation == ROC_AC_MODE_RELU;
+  if (!force_simt()) {
+    int rc = tc_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, as_stream(stream));
+    if (rc != ROC_ERR_UNSUPPORTED) return rc;
+  }
+  return simt_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, as_stream(stream));
+}
+
+extern "C" size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int outDim) {
+  if (rows <= 0 || inDim <= 0 || outDim <= 0) return 0;
+  size_t a = (size_t)simt_dw_splits(rows, inDim, outDim) * (size_t)inDim * (size_t)outDim * sizeof(float);
+  size_t b = tc_dw_workspace_bytes(rows, inDim, outDim);
+  return a > b ? a : b;
+}
+
+extern "C" int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                              const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
+                              int64_t ldDX, int activation, int accumulate_dX, void* workspace,
+                              size_t workspaceBytes, roc_stream_t stream) {
+  if (!X || !W || !dY || !dW || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldDY < outDim)
+    return ROC_ERR_INVALID;
+  if (dX && ldDX < inDim) return ROC_ERR_INVALID;
+  if (activation != ROC_AC_MODE_NONE && activation != ROC_AC_MODE_RELU) return ROC_ERR_UNSUPPORTED;
+  if (rows == 0) return ROC_OK;
+  cudaStream_t st = as_stream(stream);
+  if (activation == ROC_AC_MODE_RELU) {
+    if (!Y || ldY < outDim) return ROC_ERR_INVALID;
+    int rc = relu_bwd_inplace(rows, outDim, Y, ldY, dY, ldDY, st);
+    if (rc != ROC_OK) return rc;
+  }
+  if (!workspace) return ROC_ERR_INVALID;
+  int rc = ROC_ERR_UNSUPPORTED;
+  if (!force_simt())
+    rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, st);
+  if (rc == ROC_ERR_UNSUPPORTED)
+    rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, st);
+  if (rc != ROC_OK) return rc;
+  if (dX) {
+    rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, st);
+    if (rc != ROC_OK) return rc;
+  }
+  return ROC_OK;
+}

@@ -1,0 +1,497 @@
+// sg.cu — ScatterGather (CSR row-parallel SpMM, sum aggregation) for sm_100a.
+//
+// Replaces aggre_coop_kernel + ScatterGather::{forward,backward}_task
+// (reference scattergather_kernel.cu:20-76, 78-170).  The reference walks one
+// edge per H-thread group per iteration and accumulates with shared-memory
+// float atomics; this is a different algorithm built for HBM3e:
+//
+//  * edge-balanced schedule ("plan"): the partition's edge array is cut into
+//    CH = 64-edge chunks; one WORKER (a group of L = min(32, H/4) lanes) owns
+//    chunk c.  A row is owned by the chunk its first edge lies in.  Rows no
+//    longer than CH are always finished by their owner (so a worker does at
+//    most 2*CH-1 edges); a longer ("heavy") row is cut at chunk boundaries: the
+//    owner stores its raw partial, every later chunk stores its part into a
+//    carry slot and a second small kernel adds partial + carries in chunk
+//    order.  No atomics anywhere => bit-reproducible sums (the reference is not:
+//    smem atomicAdd, scattergather_kernel.cu:66).
+//  * the worker's col indices are loaded coalesced 32 edges at a time and
+//    broadcast with sub-warp shuffles; U independent 16-byte row gathers per
+//    lane are issued back to back regardless of row boundaries (the gathers of
+//    a run of short rows overlap), then accumulated in registers in edge order
+//    with a worker-uniform row-boundary test.
+//  * each lane owns 4 consecutive floats (LDG.128): a warp instruction fetches
+//    32/L full neighbour rows, every 32-byte sector fully used.
+//  * the store applies the ops the model puts right after scatter_gather
+//    (indegree_norm, relu; gnn.cc:83-85) so the N x H result is written once.
+//
+// Algorithmic bytes per launch: E*(4H+4) + Nloc*(4H+8).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <new>
+#include "common.cuh"
+
+namespace roc {
+
+constexpr int SG_CH = 64;          // edges per chunk
+constexpr int SG_THREADS = 256;    // threads per CTA
+
+}  // namespace roc
+
+struct roc_sg_plan {
+  uint32_t nloc = 0, E = 0, numChunks = 0, numCarries = 0, numHeavy = 0;
+  uint32_t* rs = nullptr;         // [nloc+1]   local row starts (rs[r+1] = rowEnd[r]-colLeft)
+  uint32_t* firstRow = nullptr;   // [numChunks+1] first row whose start >= c*CH
+  uint32_t* carryIdx = nullptr;   // [numChunks+1] exclusive scan of carry-in flags
+  uint32_t* heavyRows = nullptr;  // [numHeavy]  rows with degree > CH
+  const uint32_t* col = nullptr;  // caller's colSrc
+  float* carry = nullptr;         // [numCarries][carryLd]
+  size_t carryLd = 0;
+  int device = 0;
+};
+
+namespace roc {
+
+// ------------------------------------------------------------ plan kernels ---
+
+__global__ void k_build_rs(uint32_t nloc, uint64_t colLeft, const uint64_t* __restrict__ rowEnd,
+                           uint32_t* __restrict__ rs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) rs[0] = 0;
+  if (i < nloc) rs[i + 1] = (uint32_t)(rowEnd[i] - colLeft);
+}
+
+__global__ void k_first_row(uint32_t nloc, uint32_t numChunks, const uint32_t* __restrict__ rs,
+                            uint32_t* __restrict__ firstRow) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > numChunks) return;
+  if (c == numChunks) { firstRow[c] = nloc; return; }
+  uint32_t target = c * (uint32_t)SG_CH;
+  uint32_t lo = 0, hi = nloc;  // first r in [0,nloc) with rs[r] >= target, else nloc
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (rs[mid] >= target) hi = mid; else lo = mid + 1;
+  }
+  firstRow[c] = lo;
+}
+
+__global__ void k_carry_flag(uint32_t numChunks, const uint32_t* __restrict__ rs,
+                             const uint32_t* __restrict__ firstRow, uint32_t* __restrict__ flag) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > numChunks) return;
+  uint32_t f = 0;
+  if (c < numChunks) {
+    uint32_t r0 = firstRow[c];
+    if (r0 > 0) {
+      uint32_t pe = rs[r0], ps = rs[r0 - 1];
+      f = (pe > c * (uint32_t)SG_CH && pe - ps > (uint32_t)SG_CH) ? 1u : 0u;
+    }
+  }
+  flag[c] = f;
+}
+
+__global__ void k_heavy_flag(uint32_t nloc, const uint32_t* __restrict__ rs, uint8_t* __restrict__ flag) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nloc) flag[r] = (rs[r + 1] - rs[r] > (uint32_t)SG_CH) ? 1 : 0;
+}
+
+// ----------------------------------------------------------- vector helper ---
+
+template <int VEC> struct V;
+template <> struct V<4> {
+  typedef float4 T;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T ld(const T* p) { return __ldg(p); }
+  static __device__ __forceinline__ T ld_plain(const T* p) { return *p; }
+  static __device__ __forceinline__ void st(T* p, const T& v) { *p = v; }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  static __device__ __forceinline__ T div(const T& a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+  static __device__ __forceinline__ T relu(const T& a) {
+    return make_float4(relu_nanprop(a.x), relu_nanprop(a.y), relu_nanprop(a.z), relu_nanprop(a.w));
+  }
+};
+template <> struct V<1> {
+  typedef float T;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T ld(const T* p) { return __ldg(p); }
+  static __device__ __forceinline__ T ld_plain(const T* p) { return *p; }
+  static __device__ __forceinline__ void st(T* p, const T& v) { *p = v; }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a += b; }
+  static __device__ __forceinline__ T div(const T& a, float d) { return a / d; }
+  static __device__ __forceinline__ T relu(const T& a) { return relu_nanprop(a); }
+};
+
+struct SgParams {
+  const uint32_t* rs;
+  const uint32_t* firstRow;
+  const uint32_t* carryIdx;
+  const uint32_t* heavyRows;
+  const uint32_t* col;
+  const void* in;      // [*][ldIn]  (in units of T)
+  void* out;           // [nloc][ldOut]
+  void* carry;         // [numCarries][ldC]
+  size_t ldIn, ldOut, ldC;   // in units of T (float4 or float)
+  uint32_t Q;          // valid T-columns per row
+  uint32_t E, numChunks, numHeavy;
+  int epi;
+};
+
+// ------------------------------------------------------------- main kernel ---
+// One worker (L lanes) per chunk.  Lane `lane` owns T-columns lane + ch*L.
+template <int VEC, int L, int NCH, int U>
+__global__ void __launch_bounds__(SG_THREADS)
+sg_chunk_kernel(const SgParams p) {
+  typedef typename V<VEC>::T T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  const int lane = threadIdx.x % L;
+  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
+  if (w >= p.numChunks) return;
+  const unsigned wmask = (L == 32) ? 0xffffffffu
+                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
+
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t* __restrict__ col = p.col;
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+
+  const uint32_t cb = w * CH;
+  const uint32_t ce = min(cb + CH, p.E);
+  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
+
+  // current segment state
+  uint32_t cur;           // row id of the current segment
+  uint32_t curS, curT;    // its [start, end) in the edge array
+  uint32_t segEnd;        // where this worker stops accumulating into it
+  int kind;               // 0 = carry-in part of a heavy row, 1 = complete row, 2 = cut heavy row
+  uint32_t e;             // next edge
+
+  bool carryIn = false;
+  if (r0 > 0) {
+    uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true;
+      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) return;  // nothing owned, nothing carried
+    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
+  uint32_t ee;            // end of this worker's whole edge range
+  if (r1 > r0) {
+    uint32_t s = rs[r1 - 1], t = rs[r1];
+    ee = (t - s > CH) ? min(t, ce) : t;
+  } else {
+    ee = segEnd;
+  }
+
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
+
+  auto flush = [&]() {
+    if (kind == 0) {
+      T* dst = reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) if (act[ch]) V<VEC>::st(dst + lane + ch * L, acc[ch]);
+    } else {
+      T* dst = out + (size_t)cur * p.ldOut;
+      const bool fin = (kind == 1);
+      float d = 1.0f;
+      if (fin && (p.epi & ROC_SG_EPI_NORM)) d = sqrtf((float)(curT - curS));
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) {
+        if (act[ch]) {
+          T v = acc[ch];
+          if (fin && (p.epi & ROC_SG_EPI_NORM)) v = V<VEC>::div(v, d);
+          if (fin && (p.epi & ROC_SG_EPI_RELU)) v = V<VEC>::relu(v);
+          V<VEC>::st(dst + lane + ch * L, v);
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
+  };
+  auto advance = [&]() {  // move to the next owned row
+    cur += 1; curS = curT; curT = rs[cur + 1];
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  };
+
+  for (uint32_t base = e; base < ee; base += 32) {
+    uint32_t idx[32 / L];
+#pragma unroll
+    for (int j = 0; j < 32 / L; j++) {
+      uint32_t k = base + j * L + lane;
+      idx[j] = (k < ee) ? __ldg(col + k) : 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < 32; g += U) {
+      if (base + g >= ee) break;  // worker-uniform
+      T v[U][NCH];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int k = g + u;
+        uint32_t src = __shfl_sync(wmask, idx[k / L], k % L, L);
+        const bool ok = base + k < ee;
+        const T* rowp = in + (size_t)src * p.ldIn + lane;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+          v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t ecur = base + g + u;
+        if (ecur < ee) {
+          while (ecur == segEnd) { flush(); advance(); }
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+        }
+      }
+    }
+  }
+  flush();
+  while (cur + 1 < r1) { advance(); flush(); }  // trailing zero-degree rows
+}
+
+// ----------------------------------------------------------- fix-up kernel ---
+// One worker per heavy row: out[R] = epilogue(out[R] + sum_k carry[slot0 + k]), k ascending.
+template <int VEC, int L, int NCH, int U>
+__global__ void __launch_bounds__(SG_THREADS)
+sg_fixup_kernel(const SgParams p) {
+  typedef typename V<VEC>::T T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  const int lane = threadIdx.x % L;
+  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
+  if (w >= p.numHeavy) return;
+  const uint32_t R = p.heavyRows[w];
+  const uint32_t s = p.rs[R], t = p.rs[R + 1];
+  const uint32_t c0 = s / CH, cLast = (t - 1) / CH;
+  const uint32_t n = cLast - c0;
+  const uint32_t slot0 = p.carryIdx[c0 + 1];
+  T* dst = reinterpret_cast<T*>(p.out) + (size_t)R * p.ldOut;
+  const T* cbase = reinterpret_cast<const T*>(p.carry) + (size_t)slot0 * p.ldC;
+  bool act[NCH];
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) {
+    act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+    acc[ch] = act[ch] ? V<VEC>::ld_plain(dst + lane + ch * L) : V<VEC>::zero();
+  }
+  for (uint32_t k = 0; k < n; k += U) {
+    T v[U][NCH];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++)
+        v[u][ch] = (k + u < n && act[ch]) ? V<VEC>::ld_plain(cbase + (size_t)(k + u) * p.ldC + lane + ch * L)
+                                          : V<VEC>::zero();
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (k + u < n)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+  }
+  float d = 1.0f;
+  if (p.epi & ROC_SG_EPI_NORM) d = sqrtf((float)(t - s));
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) {
+    if (act[ch]) {
+      T v = acc[ch];
+      if (p.epi & ROC_SG_EPI_NORM) v = V<VEC>::div(v, d);
+      if (p.epi & ROC_SG_EPI_RELU) v = V<VEC>::relu(v);
+      V<VEC>::st(dst + lane + ch * L, v);
+    }
+  }
+}
+
+template <int VEC, int L, int NCH, int U>
+static int launch_cfg(const SgParams& p, cudaStream_t st) {
+  constexpr int WPB = SG_THREADS / L;
+  if (p.numChunks) {
+    unsigned grid = (p.numChunks + WPB - 1) / WPB;
+    sg_chunk_kernel<VEC, L, NCH, U><<<grid, SG_THREADS, 0, st>>>(p);
+    ROC_LAUNCH_CHECK();
+  }
+  if (p.numHeavy) {
+    unsigned grid = (p.numHeavy + WPB - 1) / WPB;
+    sg_fixup_kernel<VEC, L, NCH, U><<<grid, SG_THREADS, 0, st>>>(p);
+    ROC_LAUNCH_CHECK();
+  }
+  return ROC_OK;
+}
+
+template <int VEC>
+static int dispatch(const SgParams& p, cudaStream_t st) {
+  const uint32_t Q = p.Q;
+  if (Q <= 4) return launch_cfg<VEC, 4, 1, 8>(p, st);
+  if (Q <= 8) return launch_cfg<VEC, 8, 1, 8>(p, st);
+  if (Q <= 16) return launch_cfg<VEC, 16, 1, 8>(p, st);
+  if (Q <= 32) return launch_cfg<VEC, 32, 1, 8>(p, st);
+  if (Q <= 64) return launch_cfg<VEC, 32, 2, 4>(p, st);
+  if (Q <= 128) return launch_cfg<VEC, 32, 4, 2>(p, st);
+  if (Q <= 256) return launch_cfg<VEC, 32, 8, 1>(p, st);
+  return ROC_ERR_UNSUPPORTED;
+}
+
+static int ensure_carry(roc_sg_plan* plan, size_t ldFloats) {
+  if (plan->numCarries == 0 || ldFloats <= plan->carryLd) return ROC_OK;
+  if (plan->carry) { ROC_CUDA(cudaDeviceSynchronize()); ROC_CUDA(cudaFree(plan->carry)); plan->carry = nullptr; }
+  size_t bytes = (size_t)plan->numCarries * ldFloats * sizeof(float);
+  cudaError_t e = cudaMalloc(&plan->carry, bytes);
+  if (e != cudaSuccess) { plan->carryLd = 0; return (int)e; }
+  plan->carryLd = ldFloats;
+  return ROC_OK;
+}
+
+}  // namespace roc
+
+using namespace roc;
+
+extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft,
+                                  const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
+                                  roc_stream_t stream, roc_sg_plan** planOut) {
+  if (!planOut || !rowEnd || rowRight < rowLeft) return ROC_ERR_INVALID;
+  if (roc_device_count() <= 0) return ROC_ERR_NO_DEVICE;
+  cudaStream_t st = as_stream(stream);
+  uint64_t nloc64 = (uint64_t)rowRight - rowLeft + 1;
+  if (nloc64 >= 0xFFFFFFF0ull) return ROC_ERR_UNSUPPORTED;
+  uint32_t nloc = (uint32_t)nloc64;
+  uint64_t lastEnd = 0;
+  ROC_CUDA(cudaMemcpyAsync(&lastEnd, rowEnd + (nloc - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  ROC_CUDA(cudaStreamSynchronize(st));
+  if (lastEnd < colLeft) return ROC_ERR_INVALID;
+  uint64_t E64 = lastEnd - colLeft;
+  if (E64 >= 0xFFFFFF00ull) return ROC_ERR_UNSUPPORTED;  // local edge offsets are u32
+  if (E64 > 0 && !colSrc) return ROC_ERR_INVALID;
+
+  roc_sg_plan* pl = new (std::nothrow) roc_sg_plan();
+  if (!pl) return ROC_ERR_NOMEM;
+  cudaGetDevice(&pl->device);
+  pl->nloc = nloc; pl->E = (uint32_t)E64; pl->col = colSrc;
+  pl->numChunks = pl->E / SG_CH + 1;
+  uint32_t* flag = nullptr; uint8_t* hflag = nullptr; void* tmp = nullptr; uint32_t* dcount = nullptr;
+  int rc = ROC_OK;
+  auto fail = [&](int code) { rc = code; };
+#define PL_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail((int)e_); goto done; } } while (0)
+  {
+    PL_CUDA(cudaMalloc(&pl->rs, sizeof(uint32_t) * ((size_t)nloc + 1)));
+    PL_CUDA(cudaMalloc(&pl->firstRow, sizeof(uint32_t) * ((size_t)pl->numChunks + 1)));
+    PL_CUDA(cudaMalloc(&pl->carryIdx, sizeof(uint32_t) * ((size_t)pl->numChunks + 1)));
+    PL_CUDA(cudaMalloc(&flag, sizeof(uint32_t) * ((size_t)pl->numChunks + 1)));
+    PL_CUDA(cudaMalloc(&hflag, (size_t)nloc));
+    PL_CUDA(cudaMalloc(&pl->heavyRows, sizeof(uint32_t) * (size_t)nloc));
+    PL_CUDA(cudaMalloc(&dcount, sizeof(uint32_t)));
+    const int T = 256;
+    k_build_rs<<<(nloc + T) / T, T, 0, st>>>(nloc, colLeft, rowEnd, pl->rs);
+    count_launch();
+    k_first_row<<<(pl->numChunks + 1 + T - 1) / T, T, 0, st>>>(nloc, pl->numChunks, pl->rs, pl->firstRow);
+    count_launch();
+    k_carry_flag<<<(pl->numChunks + 1 + T - 1) / T, T, 0, st>>>(pl->numChunks, pl->rs, pl->firstRow, flag);
+    count_launch();
+    k_heavy_flag<<<(nloc + T - 1) / T, T, 0, st>>>(nloc, pl->rs, hflag);
+    count_launch();
+    PL_CUDA(cudaGetLastError());
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, flag, pl->carryIdx, (int)(pl->numChunks + 1), st);
+    thrust::counting_iterator<uint32_t> cnt(0);
+    cub::DeviceSelect::Flagged(nullptr, tb2, cnt, hflag, pl->heavyRows, dcount, (int)nloc, st);
+    size_t tb = tb1 > tb2 ? tb1 : tb2;
+    PL_CUDA(cudaMalloc(&tmp, tb ? tb : 16));
+    PL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, flag, pl->carryIdx, (int)(pl->numChunks + 1), st));
+    PL_CUDA(cub::DeviceSelect::Flagged(tmp, tb2, cnt, hflag, pl->heavyRows, dcount, (int)nloc, st));
+    count_launch(4);
+    PL_CUDA(cudaMemcpyAsync(&pl->numCarries, pl->carryIdx + pl->numChunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(&pl->numHeavy, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaStreamSynchronize(st));
+  }
+done:
+#undef PL_CUDA
+  cudaFree(flag); cudaFree(hflag); cudaFree(tmp); cudaFree(dcount);
+  if (rc != ROC_OK) { roc_sg_plan_destroy(pl); return rc; }
+  *planOut = pl;
+  return ROC_OK;
+}
+
+extern "C" void roc_sg_plan_destroy(roc_sg_plan* pl) {
+  if (!pl) return;
+  cudaFree(pl->rs); cudaFree(pl->firstRow); cudaFree(pl->carryIdx); cudaFree(pl->heavyRows); cudaFree(pl->carry);
+  delete pl;
+}
+
+extern "C" int roc_sg_plan_reserve(roc_sg_plan* pl, int maxH) {
+  if (!pl || maxH <= 0) return ROC_ERR_INVALID;
+  return ensure_carry(pl, ((size_t)maxH + 3) / 4 * 4);
+}
+
+extern "C" int roc_sg_plan_info(const roc_sg_plan* pl, uint64_t* numChunks, uint64_t* numCarries,
+                                uint64_t* numHeavyRows) {
+  if (!pl) return ROC_ERR_INVALID;
+  if (numChunks) *numChunks = pl->numChunks;
+  if (numCarries) *numCarries = pl->numCarries;
+  if (numHeavyRows) *numHeavyRows = pl->numHeavy;
+  return ROC_OK;
+}
+
+extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float* in, int64_t ldIn,
+                                      float* out, int64_t ldOut, int epilogue, roc_stream_t stream) {
+  roc_sg_plan* pl = const_cast<roc_sg_plan*>(plc);
+  if (!pl || H <= 0 || !in || !out || ldIn < H || ldOut < H) return ROC_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const bool vec = (ldIn % 4 == 0) && (ldOut % 4 == 0) && aligned16(in) && aligned16(out);
+  // column blocks: the widest kernel covers 256 T-columns (1024 floats vectorised, 256 scalar)
+  const int blockCols = vec ? 1024 : 256;
+  {
+    int need = H < blockCols ? H : blockCols;
+    int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4);
+    if (rc != ROC_OK) return rc;
+  }
+  for (int c0 = 0; c0 < H; c0 += blockCols) {
+    int hb = (H - c0 < blockCols) ? H - c0 : blockCols;
+    SgParams p;
+    p.rs = pl->rs; p.firstRow = pl->firstRow; p.carryIdx = pl->carryIdx; p.heavyRows = pl->heavyRows;
+    p.col = pl->col; p.in = in + c0; p.out = out + c0; p.carry = pl->carry;
+    p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.epi = epilogue;
+    int rc;
+    if (vec) {
+      p.ldIn = (size_t)ldIn / 4; p.ldOut = (size_t)ldOut / 4; p.ldC = pl->carryLd / 4;
+      p.Q = ((uint32_t)hb + 3) / 4;
+      rc = dispatch<4>(p, st);
+    } else {
+      p.ldIn = (size_t)ldIn; p.ldOut = (size_t)ldOut; p.ldC = pl->carryLd;
+      p.Q = (uint32_t)hb;
+      rc = dispatch<1>(p, st);
+    }
+    if (rc != ROC_OK) return rc;
+  }
+  return ROC_OK;
+}
+
+extern "C" int roc_sg_forward(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, int H,
+                              const roc_eid_t* rowEnd, const roc_vid_t* colSrc, const float* in,
+                              float* out, roc_stream_t stream) {
+  roc_sg_plan* pl = nullptr;
+  int rc = roc_sg_plan_create(rowLeft, rowRight, colLeft, rowEnd, colSrc, stream, &pl);
+  if (rc != ROC_OK) return rc;
+  rc = roc_sg_forward_planned(pl, H, in, H, out, H, ROC_SG_EPI_NONE, stream);
+  cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+  roc_sg_plan_destroy(pl);
+  if (rc != ROC_OK) return rc;
+  return (int)e;
+}
+
+extern "C" int roc_sg_backward(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, int H,
+                               const roc_eid_t* rowEnd, const roc_vid_t* colSrc, const float* outGrad,
+                               float* inGrad, roc_stream_t stream) {
+  // Forward and backward do exactly the same thing (scattergather_kernel.cu:168-169).
+  return roc_sg_forward(rowLeft, rowRight, colLeft, H, rowEnd, colSrc, outGrad, inGrad, stream);
+}
