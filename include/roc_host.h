@@ -76,6 +76,10 @@ int roc_host_update(roc_host* h);
 /* one full training epoch: zero_gradients; forward; backward; update */
 int roc_host_train_epoch(roc_host* h);
 int roc_host_metrics(roc_host* h, roc_perf_metrics* out);
+/* Per-launch device time of the ScatterGather kernels (CUDA events on the host's
+ * stream around each roc_sg_forward_planned): enable, run steps, read {H, ms}. */
+int roc_host_profile_sg(roc_host* h, int on);
+int roc_host_profile_sg_read(roc_host* h, int maxEntries, int* H, float* ms);
 
 #ifdef __cplusplus
 }

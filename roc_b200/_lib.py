@@ -120,6 +120,8 @@ PROTOTYPES = {
     "roc_host_update": (i32, [vp]),
     "roc_host_train_epoch": (i32, [vp]),
     "roc_host_metrics": (i32, [vp, vp]),
+    "roc_host_profile_sg": (i32, [vp, i32]),
+    "roc_host_profile_sg_read": (i32, [vp, i32, vp, vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -167,6 +167,26 @@ int roc_host_train_epoch(roc_host* h) {
   m.update();
   return 0;
 }
+int roc_host_profile_sg(roc_host* h, int on) {
+  RuntimeImpl* rt = h->rt->impl;
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  for (auto& t : rt->sgTimings) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  rt->sgTimings.clear();
+  rt->profileSg = on != 0;
+  return 0;
+}
+int roc_host_profile_sg_read(roc_host* h, int maxEntries, int* H, float* ms) {
+  RuntimeImpl* rt = h->rt->impl;
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  int n = 0;
+  for (auto& t : rt->sgTimings) {
+    if (n >= maxEntries) break;
+    float e = 0.f;
+    ROC_CHECK(cudaEventElapsedTime(&e, t.a, t.b));
+    H[n] = t.H; ms[n] = e; n++;
+  }
+  return n;
+}
 int roc_host_metrics(roc_host* h, roc_perf_metrics* out) { *out = h->m().last_metrics(); return 0; }
 
 }  // extern "C"

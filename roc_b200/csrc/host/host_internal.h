@@ -71,6 +71,12 @@ struct RuntimeImpl {
   roc_perf_metrics* d_perf = nullptr;
   roc_perf_metrics h_perf{};
   uint32_t trainStep = 0;
+  // optional per-launch timing of the ScatterGather kernels (bench.py's roofline leg)
+  struct SgTiming { int H; cudaEvent_t a, b; };
+  bool profileSg = false;
+  std::vector<SgTiming> sgTimings;
+  void sg_begin(int H);
+  void sg_end();
 
   void* dmalloc(size_t bytes);
   void dfree_all();

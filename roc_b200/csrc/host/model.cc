@@ -440,8 +440,10 @@ void ScatterGather::forward(const Model& model) {
   const int64_t ldIn = rt->t(inputs[0].region).ld;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
   const float* src = gathered(model, rt->data(inputs[0].region), ldIn);
-  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, rt->data(outRegion), rt->t(outRegion).ld,
-                                   epilogue, rt->stream));
+  float* dst = rt->data(outRegion);
+  rt->sg_begin(H);
+  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, dst, rt->t(outRegion).ld, epilogue, rt->stream));
+  rt->sg_end();
 }
 
 void ScatterGather::backward(const Model& model) {
@@ -453,8 +455,10 @@ void ScatterGather::backward(const Model& model) {
   const int dstRegion = bwdOut >= 0 ? bwdOut : inputs[0].region;
   // Forward and backward do exactly the same thing, on gradients (scattergather_kernel.cu:168-169)
   const float* src = gathered(model, rt->grad(outputs[0].region), ld);
-  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, rt->grad(dstRegion), rt->t(dstRegion).ld,
-                                   bwdEpilogue, rt->stream));
+  float* dst = rt->grad(dstRegion);
+  rt->sg_begin(H);
+  ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, dst, rt->t(dstRegion).ld, bwdEpilogue, rt->stream));
+  rt->sg_end();
 }
 
 // --------------------------------------------------------- InDegreeNorm -----

@@ -68,6 +68,18 @@ void RuntimeImpl::ensure_gather(size_t floats) {
   gatherFloats = floats;
 }
 
+void RuntimeImpl::sg_begin(int H) {
+  if (!profileSg) return;
+  SgTiming t; t.H = H;
+  ROC_CHECK(cudaEventCreate(&t.a)); ROC_CHECK(cudaEventCreate(&t.b));
+  ROC_CHECK(cudaEventRecord(t.a, stream));
+  sgTimings.push_back(t);
+}
+void RuntimeImpl::sg_end() {
+  if (!profileSg || sgTimings.empty()) return;
+  ROC_CHECK(cudaEventRecord(sgTimings.back().b, stream));
+}
+
 void RuntimeImpl::ensure_lin_ws(size_t bytes) {
   if (bytes <= linWsBytes) return;
   linWs = dmalloc(bytes);

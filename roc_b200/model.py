@@ -204,6 +204,15 @@ class Model:
     def train_epoch(self):
         check(lib.roc_host_train_epoch(self.h))
 
+    def profile_sg(self, on=True):
+        check(lib.roc_host_profile_sg(self.h, int(on)))
+
+    def profile_sg_read(self, max_entries=4096):
+        hs = (C.c_int * max_entries)()
+        ms = (C.c_float * max_entries)()
+        n = lib.roc_host_profile_sg_read(self.h, max_entries, hs, ms)
+        return [(int(hs[i]), float(ms[i])) for i in range(n)]
+
     def metrics(self):
         pm = PerfMetrics()
         check(lib.roc_host_metrics(self.h, C.byref(pm)))

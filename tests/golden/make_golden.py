@@ -142,7 +142,8 @@ def main():
     G["add_out"] = ref.add_fwd(torch.from_numpy(a).to(dev), torch.from_numpy(gy).to(dev)).cpu().numpy()
 
     # ---- Glorot init (cuRAND XORWOW seeded like initializer_kernel.cu:40-48)
-    for seed, (i_dim, o_dim) in ((1804289383, (16, 16)), (846930886, (602, 64))):
+    # glibc: srand(1); rand() -> 1804289383, 846930886 (gnn.cc:56 + initializer.cc:38)
+    for seed, (i_dim, o_dim) in ((1804289383, (16, 16)), (846930886, (16, 5)), (1804289383, (602, 64))):
         G["glorot_%d_%dx%d" % (seed, i_dim, o_dim)] = ref.glorot(i_dim, o_dim, seed).cpu().numpy()
 
     path = os.path.join(outdir, "ref_golden.npz")

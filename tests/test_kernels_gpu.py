@@ -1,0 +1,318 @@
+"""GPU suite, part 1: every C-ABI kernel against the oracle on the same seeded
+inputs, against the golden vectors minted from the reference's kernels, and (when
+oracle/_ref is present) against the reference kernels run side by side.
+Bit-exact for indices / masks / partition bounds; 1e-4 relative for fp32 tensors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_close
+from oracle import oracle, ref
+from roc_b200 import _lib, datasets
+from roc_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def to_dev(row_end, col):
+    return (torch.from_numpy(np.asarray(row_end).astype(np.int64)).to(DEV),
+            torch.from_numpy(np.asarray(col).astype(np.int32)).to(DEV))
+
+
+def graph(kind):
+    if kind == "uniform":
+        re, col = datasets.uniform_graph(1000, 4500, seed=1)
+    elif kind == "rmat":
+        re, col = datasets.rmat_graph(12, 40000, seed=3)           # hubs with degree >> 64
+    elif kind == "dense":
+        re, col = datasets.powerlaw_graph(600, 60000, seed=4)      # mean degree ~150: every row heavy
+    elif kind == "ragged":
+        # empty rows, a 1-edge graph tail, one 5000-edge row
+        deg = np.zeros(400, dtype=np.int64)
+        deg[3] = 5000; deg[10:200:7] = 1; deg[250] = 63; deg[251] = 64; deg[252] = 65; deg[399] = 2
+        re = torch.from_numpy(np.cumsum(deg))
+        col = torch.from_numpy(np.random.RandomState(9).randint(0, 400, size=int(deg.sum())).astype(np.int32))
+    elif kind == "single":
+        re, col = torch.tensor([1]), torch.tensor([0], dtype=torch.int32)
+    else:
+        raise KeyError(kind)
+    return re.numpy().astype(np.uint64), col.numpy().astype(np.uint32)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rmat", "dense", "ragged", "single"])
+@pytest.mark.parametrize("h", [1, 4, 16, 41, 64, 100, 128, 256, 602])
+def test_sg_planned_vs_oracle(kind, h):
+    row_end, col = graph(kind)
+    n = row_end.shape[0]
+    x = np.random.RandomState(h).randn(n, h).astype(np.float32)
+    want = oracle.scatter_gather(0, n - 1, 0, row_end, col, x)
+    d_re, d_col = to_dev(row_end, col)
+    plan = K.SgPlan(0, n - 1, 0, d_re, d_col)
+    xp = K.padded(n, h, DEV, fill=torch.from_numpy(x).to(DEV))     # ld = round_up(h, 4): vector path
+    got = plan.forward(xp)
+    torch.cuda.synchronize()
+    rel_close(got.cpu().numpy(), want, what="%s H=%d padded" % (kind, h))
+    xd = torch.from_numpy(x).to(DEV)                              # dense ld = h: scalar path when h % 4
+    got2 = plan.forward(xd, out=torch.empty((n, h), device=DEV))
+    rel_close(got2.cpu().numpy(), want, what="%s H=%d dense" % (kind, h))
+    # determinism: same plan, same input -> identical bits
+    assert torch.equal(plan.forward(xp), got)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rmat", "dense"])
+def test_sg_epilogues(kind):
+    row_end, col = graph(kind)
+    n, h = row_end.shape[0], 64
+    x = np.random.RandomState(1).randn(n, h).astype(np.float32)
+    d_re, d_col = to_dev(row_end, col)
+    plan = K.SgPlan(0, n - 1, 0, d_re, d_col)
+    xd = torch.from_numpy(x).to(DEV)
+    raw = plan.forward(xd).cpu().numpy()
+    normed = oracle.indegree_norm(0, n - 1, 0, row_end, raw)
+    got = plan.forward(xd, epilogue=_lib.SG_EPI_NORM).cpu().numpy()
+    assert np.array_equal(got, normed), "fused norm must equal norm applied to the kernel's own sum"
+    got = plan.forward(xd, epilogue=_lib.SG_EPI_NORM | _lib.SG_EPI_RELU).cpu().numpy()
+    assert np.array_equal(got, np.maximum(normed, 0))
+
+
+def test_sg_partition_slices_and_planless_abi():
+    row_end, col = graph("rmat")
+    n, h = row_end.shape[0], 16
+    x = np.random.RandomState(2).randn(n, h).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    for parts in (2, 4):
+        k, vb, eb = oracle.partition(row_end, parts)
+        assert k == parts
+        for c in range(parts):
+            rl, rr, cl, cr = int(vb[c, 0]), int(vb[c, 1]), int(eb[c, 0]), int(eb[c, 1])
+            d_re, d_col = to_dev(row_end[rl:rr + 1], col[cl:cr + 1])
+            want = oracle.scatter_gather(rl, rr, cl, row_end[rl:rr + 1], col[cl:cr + 1], x)
+            got = K.sg_forward(rl, rr, cl, d_re, d_col, xd)
+            rel_close(got.cpu().numpy(), want, what="planless part %d/%d" % (c, parts))
+            got_b = K.sg_backward(rl, rr, cl, d_re, d_col, xd)
+            assert torch.equal(got, got_b)          # forward and backward are the same op (Q1)
+
+
+def test_sg_plan_info_counts():
+    row_end, col = graph("ragged")
+    d_re, d_col = to_dev(row_end, col)
+    plan = K.SgPlan(0, row_end.shape[0] - 1, 0, d_re, d_col)
+    info = plan.info()
+    e = int(row_end[-1])
+    assert info["chunks"] == e // 64 + 1
+    deg = np.diff(np.concatenate([[0], row_end.astype(np.int64)]))
+    assert info["heavy_rows"] == int((deg > 64).sum())
+
+
+def test_sg_invalid_arguments():
+    row_end, col = graph("uniform")
+    d_re, d_col = to_dev(row_end, col)
+    plan = K.SgPlan(0, row_end.shape[0] - 1, 0, d_re, d_col)
+    x = torch.zeros((1000, 8), device=DEV)
+    assert _lib.lib.roc_sg_forward_planned(plan.handle, 0, x.data_ptr(), 8, x.data_ptr(), 8, 0, None) == _lib.ROC_ERR_INVALID
+    assert _lib.lib.roc_sg_forward_planned(plan.handle, 8, None, 8, x.data_ptr(), 8, 0, None) == _lib.ROC_ERR_INVALID
+    assert _lib.lib.roc_sg_forward_planned(plan.handle, 8, x.data_ptr(), 4, x.data_ptr(), 8, 0, None) == _lib.ROC_ERR_INVALID
+
+
+def test_sg_round_trip_properties_large():
+    """Size-independent properties at a size the oracle would take too long on:
+    linearity, A(1) = degree, and agreement with torch's own sparse matmul."""
+    re, col = datasets.rmat_graph(18, 2_000_000, seed=5, device=DEV)
+    n = re.shape[0]
+    plan = K.SgPlan(0, n - 1, 0, re, col)
+    h = 64
+    g = torch.Generator(device=DEV); g.manual_seed(1)
+    x = torch.rand((n, h), device=DEV, generator=g) - 0.5
+    y = torch.rand((n, h), device=DEV, generator=g) - 0.5
+    ax, ay, axy = plan.forward(x), plan.forward(y), plan.forward(x + 2 * y)
+    assert torch.allclose(axy, ax + 2 * ay, rtol=1e-4, atol=1e-4)
+    deg = torch.diff(re, prepend=torch.zeros(1, dtype=re.dtype, device=DEV)).to(torch.float32)
+    ones = plan.forward(torch.ones((n, 4), device=DEV))
+    assert torch.equal(ones[:, 0], deg)
+    crow = torch.cat([torch.zeros(1, dtype=torch.int64, device=DEV), re])
+    a = torch.sparse_csr_tensor(crow, col.to(torch.int64), torch.ones(col.shape[0], device=DEV), size=(n, n))
+    want = a @ x
+    assert torch.allclose(ax, want, rtol=1e-4, atol=1e-4)
+
+
+def test_build_csr_bit_exact():
+    row_end, col = graph("rmat")
+    k, vb, eb = oracle.partition(row_end, 3)
+    for c in range(3):
+        rl, rr, cl, cr = int(vb[c, 0]), int(vb[c, 1]), int(eb[c, 0]), int(eb[c, 1])
+        d_re, d_col = to_dev(row_end[rl:rr + 1], col[cl:cr + 1])
+        rp, es, cs = K.build_csr(rl, rr, cl, d_re, d_col)
+        wrp, wes = oracle.build_csr(rl, rr, cl, row_end[rl:rr + 1], col[cl:cr + 1])
+        assert np.array_equal(rp.cpu().numpy().astype(np.uint64), wrp)
+        assert np.array_equal(es.cpu().numpy().astype(np.uint32), wes)
+        assert np.array_equal(cs.cpu().numpy().astype(np.uint32), col[cl:cr + 1])
+
+
+@pytest.mark.parametrize("h", [1, 16, 41, 64])
+def test_indegree_norm_bit_exact(h):
+    row_end, col = graph("rmat")
+    n = row_end.shape[0]
+    x = np.random.RandomState(h).randn(n, h).astype(np.float32)
+    k, vb, eb = oracle.partition(row_end, 2)
+    for c in range(2):
+        rl, rr, cl = int(vb[c, 0]), int(vb[c, 1]), int(eb[c, 0])
+        d_re, _ = to_dev(row_end[rl:rr + 1], col[:1])
+        want = oracle.indegree_norm(rl, rr, cl, row_end[rl:rr + 1], x[rl:rr + 1])
+        for xin in (torch.from_numpy(x[rl:rr + 1]).to(DEV), K.padded(rr - rl + 1, h, DEV, fill=torch.from_numpy(x[rl:rr + 1]).to(DEV))):
+            got = K.indegree_norm(rl, rr, cl, d_re, xin)
+            assert np.array_equal(got.cpu().numpy(), want)
+    # fused relu-mask backward
+    y = np.random.RandomState(7).randn(n, h).astype(np.float32)
+    d_re, _ = to_dev(row_end, col[:1])
+    got = K.indegree_norm(0, n - 1, 0, d_re, torch.from_numpy(x).to(DEV), relu_mask_of=torch.from_numpy(y).to(DEV))
+    want = oracle.indegree_norm(0, n - 1, 0, row_end, np.where(y > 0, x, 0).astype(np.float32))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_activation_add():
+    r = np.random.RandomState(3)
+    x, dy = r.randn(333, 41).astype(np.float32), r.randn(333, 41).astype(np.float32)
+    for mode in (1, 2):
+        y = K.activation_fwd(torch.from_numpy(x).to(DEV), mode)
+        wy = oracle.activation_fwd(x, mode)
+        rel_close(y.cpu().numpy(), wy, rtol=1e-6, what="act fwd")
+        dx = K.activation_bwd(y, torch.from_numpy(dy).to(DEV), mode)
+        rel_close(dx.cpu().numpy(), oracle.activation_bwd(y.cpu().numpy(), dy, mode), rtol=1e-6, what="act bwd")
+        acc = torch.full_like(y, 0.5)
+        K.activation_bwd(y, torch.from_numpy(dy).to(DEV), mode, dx=acc)
+        rel_close(acc.cpu().numpy(), 0.5 + dx.cpu().numpy(), rtol=1e-6, what="act bwd accumulate")
+    s = K.add_fwd(torch.from_numpy(x).to(DEV), torch.from_numpy(dy).to(DEV))
+    assert np.array_equal(s.cpu().numpy(), x + dy)
+    da, db = torch.zeros_like(s), torch.ones_like(s)
+    K.add_bwd(s, da, False, db, True)
+    assert torch.equal(da, s) and torch.equal(db, s + 1)
+
+
+@pytest.mark.parametrize("h,rate", [(602, 0.5), (64, 0.5), (41, 0.1), (16, 0.0)])
+def test_dropout_mask_bit_exact(h, rate):
+    rows, first = 257, 1000
+    x = np.random.RandomState(1).randn(rows, h).astype(np.float32)
+    keep = oracle.dropout_mask(first * h, rows * h, rate, (5 << 32) | 3, 9).reshape(rows, h)
+    want = oracle.dropout_apply(x, keep, rate)
+    for xin in (torch.from_numpy(x).to(DEV), K.padded(rows, h, DEV, fill=torch.from_numpy(x).to(DEV))):
+        got = K.dropout_fwd(xin, first, rate, (5 << 32) | 3, 9)
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_softmax_xent_both_label_forms():
+    r = np.random.RandomState(4)
+    for n, c in ((500, 7), (1000, 41), (64, 47), (10, 1)):
+        logits = (r.randn(n, c) * 2).astype(np.float32)
+        lab = r.randint(0, c, size=n).astype(np.int32)
+        mask = r.randint(0, 4, size=n).astype(np.int32)
+        oh = datasets.onehot(lab, c)
+        wg, wp = oracle.softmax_xent_bwd(logits, oh, mask)
+        for compact in (False, True):
+            labels = torch.from_numpy(lab).to(DEV) if compact else torch.from_numpy(oh).to(DEV)
+            g, p = K.softmax_xent_bwd(K.padded(n, c, DEV, fill=torch.from_numpy(logits).to(DEV)), labels,
+                                      torch.from_numpy(mask).to(DEV), compact=compact)
+            rel_close(g.cpu().numpy(), wg, what="softmax grad")
+            assert abs(p["trainLoss"] - wp["trainLoss"]) <= 1e-4 * max(abs(wp["trainLoss"]), 1.0)
+            for k in ("trainAll", "testAll", "valAll", "trainCorrect", "testCorrect", "valCorrect"):
+                assert p[k] == wp[k], (k, p, wp)
+
+
+@pytest.mark.parametrize("n,i,o", [(200, 33, 9), (1000, 602, 64), (777, 64, 41), (129, 16, 16), (5, 3, 2)])
+def test_linear_fwd_bwd(n, i, o):
+    r = np.random.RandomState(n)
+    x, w, dy = r.randn(n, i).astype(np.float32), (r.randn(o, i) * 0.1).astype(np.float32), r.randn(n, o).astype(np.float32)
+    xp = K.padded(n, i, DEV, fill=torch.from_numpy(x).to(DEV))
+    wd = torch.from_numpy(w).to(DEV)
+    for act in (0, 1):
+        y = K.linear_fwd(xp, wd, activation=act)
+        wy = oracle.linear_fwd(x, w, relu=bool(act))
+        rel_close(y.cpu().numpy(), wy, what="linear fwd")
+        gy = K.padded(n, o, DEV, fill=torch.from_numpy(dy).to(DEV))
+        dw = torch.ones_like(wd)
+        dx = K.padded(n, i, DEV)
+        K.linear_bwd(xp, wd, y, gy, dw, dx, activation=act)
+        wdw = np.ones_like(w)
+        wgy = dy.copy()
+        wdx = oracle.linear_bwd(x, w, wy, wgy, wdw, relu=bool(act))
+        rel_close(dw.cpu().numpy(), wdw, what="dW")
+        rel_close(dx.cpu().numpy(), wdx, what="dX")
+        assert np.array_equal(gy.cpu().numpy(), wgy)      # relu mask applied in place
+        K.linear_bwd(xp, wd, y, gy, dw, dx, activation=0, accumulate_dx=True)
+        rel_close(dx.cpu().numpy(), 2 * wdx, what="dX accumulate")
+
+
+def test_linear_norm_epilogue():
+    row_end, col = graph("uniform")
+    n = row_end.shape[0]
+    r = np.random.RandomState(8)
+    x, w = r.randn(n, 24).astype(np.float32), r.randn(16, 24).astype(np.float32)
+    d_re, _ = to_dev(row_end, col[:1])
+    y = K.linear_fwd(torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV))
+    yn = K.linear_fwd(torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), norm_row_end=d_re, col_left=0)
+    want = oracle.indegree_norm(0, n - 1, 0, row_end, np.ascontiguousarray(y.cpu().numpy()))
+    assert np.array_equal(yn.cpu().numpy(), want)
+
+
+def test_adam():
+    r = np.random.RandomState(6)
+    w, g = r.randn(38528).astype(np.float32), r.randn(38528).astype(np.float32)
+    m, v = (r.randn(38528) * 0.1).astype(np.float32), np.abs(r.randn(38528) * 0.1).astype(np.float32)
+    ww, wm, wv = w.copy(), m.copy(), v.copy()
+    oracle.adam_update(ww, g, wm, wv, np.float32(0.003), np.float32(0.9), np.float32(0.999), np.float32(0.05), np.float32(1e-8))
+    dw, dg, dm, dv = (torch.from_numpy(t.copy()).to(DEV) for t in (w, g, m, v))
+    K.adam_update(dw, dg, dm, dv, 0.003, 0.9, 0.999, 0.05, 1e-8)
+    rel_close(dw.cpu().numpy(), ww, rtol=1e-6, what="adam w")
+    rel_close(dm.cpu().numpy(), wm, rtol=1e-6, what="adam m")
+    rel_close(dv.cpu().numpy(), wv, rtol=1e-6, what="adam v")
+
+
+# ---------------------------------------------- golden vectors from the reference ---
+def test_kernels_vs_reference_golden(golden):
+    g = golden
+    re, col = g["A_row_end"], g["A_col"]
+    n = re.shape[0]
+    d_re, d_col = to_dev(re, col)
+    plan = K.SgPlan(0, n - 1, 0, d_re, d_col)
+    for h in (16, 41, 64):
+        x = torch.from_numpy(g["A_sg_in_%d" % h]).to(DEV)
+        rel_close(plan.forward(x, out=torch.empty((n, h), device=DEV)).cpu().numpy(), g["A_sg_out_%d" % h],
+                  what="vs aggre_coop_kernel H=%d" % h)
+        assert np.array_equal(K.indegree_norm(0, n - 1, 0, d_re, x).cpu().numpy(), g["A_norm_out_%d" % h])
+    rp, es, _ = K.build_csr(0, n - 1, 0, d_re, d_col)
+    assert np.array_equal(es.cpu().numpy().astype(np.uint32), g["A_edgestructs"])
+    x, w, dy = (torch.from_numpy(g[k]).to(DEV) for k in ("lin_X", "lin_W", "lin_dY"))
+    for relu in (0, 1):
+        y = K.linear_fwd(x, w, activation=relu, out=torch.empty((x.shape[0], w.shape[0]), device=DEV))
+        rel_close(y.cpu().numpy(), g["lin_Y_relu%d" % relu], what="vs cublasSgemm fwd")
+        dw, dx, gy = torch.zeros_like(w), torch.zeros_like(x), dy.clone()
+        K.linear_bwd(x, w, y, gy, dw, dx, activation=relu)
+        rel_close(dw.cpu().numpy(), g["lin_dW_relu%d" % relu], what="vs cublasSgemm dW")
+        rel_close(dx.cpu().numpy(), g["lin_dX_relu%d" % relu], what="vs cublasSgemm dX")
+    grad, perf = K.softmax_xent_bwd(torch.from_numpy(g["sm_logits"]).to(DEV),
+                                    torch.from_numpy(datasets.onehot(g["sm_labels"], 7)).to(DEV),
+                                    torch.from_numpy(g["sm_mask"]).to(DEV))
+    rel_close(grad.cpu().numpy(), g["sm_grad"], what="vs cudnnSoftmax+softmax_backward")
+    assert [perf[k] for k in ("trainAll", "testAll", "valAll", "trainCorrect", "testCorrect", "valCorrect")] == \
+        [int(v) for v in g["sm_perf"][1:]]
+    dw, dg, dm, dv = (torch.from_numpy(g[k].copy()).to(DEV) for k in ("adam_w", "adam_gsum", "adam_m", "adam_v"))
+    K.adam_update(dw, dg, dm, dv, 0.01, 0.9, 0.999, 0.05, 1e-8)
+    rel_close(dw.cpu().numpy(), g["adam_w_out"], rtol=1e-6, what="vs adam_update")
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libroc_ref.so not built (no /root/reference here)")
+def test_side_by_side_with_reference_kernel():
+    re_t, col_t = datasets.rmat_graph(14, 150000, seed=8)
+    row_end, col = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
+    n = row_end.shape[0]
+    d_re, d_col = to_dev(row_end, col)
+    rp, es = ref.edge_structs(d_col, d_re, 0, 0)
+    plan = K.SgPlan(0, n - 1, 0, d_re, d_col)
+    for h in (16, 64, 128, 256):
+        x = torch.rand((n, h), device=DEV) - 0.5
+        want = ref.scatter_gather(0, n - 1, 0, rp, es, x)
+        got = plan.forward(x)
+        torch.cuda.synchronize()
+        rel_close(got.cpu().numpy(), want.cpu().numpy(), what="vs live aggre_coop_kernel H=%d" % h)

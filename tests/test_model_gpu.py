@@ -1,0 +1,155 @@
+"""GPU suite, part 2: the host (Model / op-builder API over the C-ABI kernels)
+against the oracle's GCN on the same graph, features, labels, masks and weights —
+forward logits, every dW, and the weights after several Adam steps.  Covers
+BASELINE.json configs[0] (1K-node / 10K-edge, 16 -> 16), the residual variant
+(more than 3 layer dims), dropout with the shared Philox mask, fused vs unfused
+schedules, the dataset file loaders and the stand-alone driver."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_close
+from oracle import oracle
+from roc_b200 import _lib, datasets
+from roc_b200.model import Host, Model, build_gcn
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(n=1000, pairs=4500, layers=(16, 16, 5), seed=1):
+    re_t, col_t = datasets.uniform_graph(n, pairs, seed=seed)
+    row_end, col = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
+    feats, labels, mask = datasets.node_data(n, layers[0], layers[-1], seed=seed)
+    return row_end, col, feats.numpy(), labels.numpy(), mask.numpy()
+
+
+def run_product(row_end, col, feats, labels, mask, layers, dropout, epochs, fuse, lr=0.01, wd=0.05):
+    host = Host(0, 0, 1)
+    host.graph_from_arrays(row_end, col)
+    m = Model(host, seed=1)
+    m.set_fusion(fuse)
+    h = build_gcn(m, list(layers), dropout, lr=lr, weight_decay=wd)
+    m.set_tensor(h["input"], feats)
+    m.set_labels(h["label"], labels)
+    m.set_tensor(h["mask"], mask.astype(np.int32))
+    w0 = [m.get_parameter(p) for p in range(m.num_parameters())]
+    out = {"w0": w0, "perf": [], "logits": None, "dW": None}
+    for ep in range(epochs):
+        m.train_mode()
+        m.zero_gradients()
+        m.forward()
+        if ep == 0:
+            out["logits"] = m.get_tensor(h["logits"])
+        m.backward()
+        if ep == 0:
+            out["dW"] = [m.get_parameter(p, "grad") for p in range(m.num_parameters())]
+        out["perf"].append(m.metrics())
+        m.update()
+    out["w"] = [m.get_parameter(p) for p in range(m.num_parameters())]
+    m.infer_mode()
+    m.forward()
+    out["infer_perf"] = m.metrics()
+    host.close()
+    return out
+
+
+def run_oracle(row_end, col, feats, labels, mask, layers, dropout, epochs, w0, lr=0.01, wd=0.05):
+    o = oracle.GcnOracle(row_end, col, layers, w0, lr=lr, weight_decay=wd, dropout=dropout)
+    oh = datasets.onehot(labels, layers[-1])
+    res = {"perf": []}
+    for ep in range(epochs):
+        o.forward(feats, train=True)
+        if ep == 0:
+            res["logits"] = o.logits.copy()
+        o.backward(oh, mask)
+        if ep == 0:
+            res["dW"] = [d.copy() for d in o.dW]
+        res["perf"].append(o.perf)
+        o.update()
+    res["w"] = o.W
+    o.forward(feats, train=False)
+    _, res["infer_perf"] = oracle.softmax_xent_bwd(o.logits, oh, mask)
+    return res
+
+
+@pytest.mark.parametrize("layers,dropout", [((16, 16, 5), 0.0), ((16, 16, 5), 0.5), ((24, 32, 16, 7), 0.0),
+                                            ((24, 32, 16, 7), 0.3), ((602, 64, 41), 0.5)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_gcn_training_matches_oracle(layers, dropout, fuse):
+    case = make_case(layers=layers)
+    epochs = 4
+    got = run_product(*case, layers, dropout, epochs, fuse)
+    want = run_oracle(*case, layers, dropout, epochs, got["w0"])
+    rel_close(got["logits"], want["logits"], what="logits epoch 0")
+    for p, (a, b) in enumerate(zip(got["dW"], want["dW"])):
+        rel_close(a, b, rtol=2e-4, what="dW[%d] epoch 0" % p)
+    for ep in range(epochs):
+        gp, wp = got["perf"][ep], want["perf"][ep]
+        assert gp["trainAll"] == wp["trainAll"]
+        assert abs(gp["trainLoss"] - wp["trainLoss"]) <= 2e-4 * abs(wp["trainLoss"]), (ep, gp, wp)
+    for p, (a, b) in enumerate(zip(got["w"], want["w"])):
+        # Adam's first steps are ~sign(g)*lr, so weights track within the gradient's tolerance
+        rel_close(a, b, rtol=1e-3, atol_scale=1e-4, what="W[%d] after %d epochs" % (p, epochs))
+    assert got["infer_perf"]["trainAll"] == want["infer_perf"]["trainAll"]
+    assert got["infer_perf"]["testAll"] == want["infer_perf"]["testAll"]
+
+
+def test_fused_and_unfused_schedules_agree_bitwise():
+    case = make_case(layers=(16, 16, 5))
+    a = run_product(*case, (16, 16, 5), 0.5, 3, True)
+    b = run_product(*case, (16, 16, 5), 0.5, 3, False)
+    assert np.array_equal(a["logits"], b["logits"])
+    for x, y in zip(a["w"], b["w"]):
+        assert np.array_equal(x, y)
+
+
+def test_glorot_weights_match_reference_curand(golden):
+    """std::srand(1) then one std::rand() per linear -> cuRAND XORWOW seeds 1804289383, 846930886
+    (initializer.cc:38, initializer_kernel.cu:40-48); weights must match the reference's bit for bit."""
+    case = make_case(layers=(16, 16, 5))
+    got = run_product(*case, (16, 16, 5), 0.0, 1, True)
+    assert np.array_equal(got["w0"][0], golden["glorot_1804289383_16x16"])
+    assert np.array_equal(got["w0"][1], golden["glorot_846930886_16x5"])
+    big = make_case(n=64, pairs=100, layers=(602, 64, 3))
+    got = run_product(*big, (602, 64, 3), 0.0, 1, True)
+    assert np.array_equal(got["w0"][0], golden["glorot_1804289383_602x64"])
+
+
+def test_file_loaders_and_driver(tmp_path):
+    layers = (16, 16, 5)
+    row_end, col, feats, labels, mask = make_case(layers=layers)
+    prefix = str(tmp_path / "tiny")
+    datasets.write_dataset(prefix, row_end, col, feats, labels, mask)
+    host = Host(0, 0, 1)
+    host.graph_from_lux(prefix)
+    info = host.graph_info()
+    assert info["numNodes"] == 1000 and info["numEdges"] == col.shape[0] and info["rowRight"] == 999
+    m = Model(host, seed=1)
+    h = build_gcn(m, list(layers), 0.0)
+    m.load_features(h["input"], prefix)
+    m.load_labels(h["label"], prefix)
+    m.load_train_mask(h["mask"], prefix)
+    assert np.array_equal(m.get_tensor(h["input"]), feats)
+    assert np.array_equal(m.get_tensor(h["mask"], dtype=np.int32)[:, 0], mask)
+    m.train_epoch()
+    perf_files = m.metrics()
+    host.close()
+    got = run_product(row_end, col, feats, labels, mask, layers, 0.0, 1, True)
+    assert perf_files == got["perf"][0]
+    # CSV path: parse, then the .feats.bin cache must appear (load_task.cu:63-65)
+    prefix2 = str(tmp_path / "csv")
+    datasets.write_lux(prefix2, row_end, col)
+    datasets.write_feats_csv(prefix2, feats)
+    datasets.write_labels(prefix2, labels)
+    datasets.write_mask(prefix2, mask)
+    exe = os.path.join(ROOT, "roc_b200", "bin", "roc_gnn")
+    p = subprocess.run([exe, "-ll:gpu", "1", "-file", prefix2, "-layers", "16-16-5", "-e", "6", "-lr", "0.01",
+                        "-decay", "0.0001", "-dropout", "0.5"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert os.path.exists(prefix2 + ".feats.bin")
+    assert np.array_equal(np.fromfile(prefix2 + ".feats.bin", dtype=np.float32).reshape(feats.shape), feats)
+    lines = [l for l in p.stderr.splitlines() if "[INFER]" in l]
+    assert len(lines) == 2 and "train_accuracy" in lines[0]      # epochs 0 and 5 (gnn.cc:107-110)
