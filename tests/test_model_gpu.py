@@ -138,7 +138,12 @@ def test_file_loaders_and_driver(tmp_path):
     perf_files = m.metrics()
     host.close()
     got = run_product(row_end, col, feats, labels, mask, layers, 0.0, 1, True)
-    assert perf_files == got["perf"][0]
+    ref_perf = got["perf"][0]
+    for k in perf_files:     # the loss is summed with float atomics across CTAs: equal up to rounding
+        if k == "trainLoss":
+            assert abs(perf_files[k] - ref_perf[k]) <= 1e-5 * abs(ref_perf[k])
+        else:
+            assert perf_files[k] == ref_perf[k]
     # CSV path: parse, then the .feats.bin cache must appear (load_task.cu:63-65)
     prefix2 = str(tmp_path / "csv")
     datasets.write_lux(prefix2, row_end, col)
