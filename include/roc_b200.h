@@ -242,6 +242,10 @@ int roc_scale(int64_t count, float a, float b, float* W, roc_stream_t stream);
 /* Replaces assign_kernel, cuda_helper.cu:11-18 (zero_grad_task_impl,
  * ZerosInitializer): 2-D fill of the [rows][H] window of a [rows][ld] tensor. */
 int roc_fill(int64_t rows, int H, float value, float* x, int64_t ld, roc_stream_t stream);
+/* Replaces copy_kernel, cuda_helper.cu:20-27 (dropout's infer path, staging): 2-D copy of
+ * the [rows][H] window between tensors of different leading dimensions. */
+int roc_copy2d(int64_t rows, int H, const float* src, int64_t ldSrc, float* dst, int64_t ldDst,
+               roc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -273,7 +273,7 @@ class GcnOracle:
             sg = self._sg(n1)
             n2 = self._norm(sg)
             a = activation_fwd(n2, 1) if i != L else n2
-            rec = dict(d=d, keep=keep, rate=rate, w_main=w_main, a=a, relu=(i != L))
+            rec = dict(d=d, keep=keep, rate=rate, w_main=w_main, a=a, relu=(i != L), pre=n2)
             if self.residual:
                 rec["w_res"] = wi
                 r = linear_fwd(d, self.W[wi], False, self.acc64); wi += 1
@@ -300,7 +300,9 @@ class GcnOracle:
                                  need_dx=not first_layer, acc64=self.acc64)
             ga = g
             if rec["relu"]:
-                ga = activation_bwd(rec["a"], ga, 1)
+                # "a_override": relu output whose sign pattern the backward should use instead of the
+                # oracle's own (a test may inject the product's mask where pre-activations are ~0)
+                ga = activation_bwd(rec.get("a_override", rec["a"]), ga, 1)
             gn2 = self._norm(ga)
             gsg = self._sg(gn2)          # A, not A^T (scattergather_kernel.cu:160-170)
             gn1 = self._norm(gsg)

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "roc_adam_update": (i32, [i64, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]),
     "roc_scale": (i32, [i64, f32, f32, vp, vp]),
     "roc_fill": (i32, [i64, i32, f32, vp, i64, vp]),
+    "roc_copy2d": (i32, [i64, i32, vp, i64, vp, i64, vp]),
     # ---- roc_host.h
     "roc_host_create": (vp, [i32, i32, i32]),
     "roc_host_destroy": (None, [vp]),

@@ -538,6 +538,13 @@ extern "C" int roc_scale(int64_t count, float a, float b, float* W, roc_stream_t
   return ROC_OK;
 }
 
+extern "C" int roc_copy2d(int64_t rows, int H, const float* src, int64_t ldSrc, float* dst, int64_t ldDst,
+                          roc_stream_t stream) {
+  if (!src || !dst || rows < 0 || H <= 0 || ldSrc < H || ldDst < H) return ROC_ERR_INVALID;
+  if (rows == 0) return ROC_OK;
+  return launch_map<OP_COPY, false>(rows, H, src, ldSrc, nullptr, 0, dst, ldDst, as_stream(stream));
+}
+
 extern "C" int roc_fill(int64_t rows, int H, float value, float* x, int64_t ld, roc_stream_t stream) {
   if (!x || rows < 0 || H <= 0 || ld < H) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;

@@ -67,6 +67,7 @@ struct RuntimeImpl {
   // shared scratch
   float* gatherBuf = nullptr; size_t gatherFloats = 0;   // [numNodes][maxLd] when numParts > 1
   void* linWs = nullptr; size_t linWsBytes = 0;           // split-K workspace of Linear backward
+  void* staging = nullptr; size_t stagingBytes = 0;       // H2D staging for dense host rows -> padded rows
   float* flatGrad = nullptr; size_t flatGradCount = 0;    // all dW, one all-reduce
   roc_perf_metrics* d_perf = nullptr;
   roc_perf_metrics h_perf{};
@@ -86,6 +87,7 @@ struct RuntimeImpl {
   TensorImpl& t(int region) { return tensors[(size_t)region]; }
   void ensure_gather(size_t floats);
   void ensure_lin_ws(size_t bytes);
+  void ensure_staging(size_t bytes);
 };
 
 inline int64_t round_up4(int64_t x) { return (x + 3) / 4 * 4; }

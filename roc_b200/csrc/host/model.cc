@@ -3,6 +3,7 @@
 // forward/backward enqueues C-ABI kernels (roc_b200.h) on the Runtime's stream
 // instead of launching a Legion index task.
 #include <curand.h>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -293,8 +294,21 @@ void Model::set_tensor(const Tensor& t, const void* host, bool grad) {
   RuntimeImpl* rt = ctx;
   TensorImpl& x = rt->t(t.region);
   float* dst = grad ? rt->grad(t.region) : rt->data(t.region);
-  ROC_CHECK(cudaMemcpy2DAsync(dst, (size_t)x.ld * 4, host, (size_t)x.H * 4, (size_t)x.H * 4, (size_t)x.rows,
-                              cudaMemcpyHostToDevice, rt->stream));
+  if (x.ld == x.H || x.isInt) {
+    ROC_CHECK(cudaMemcpyAsync(dst, host, (size_t)x.rows * x.H * 4, cudaMemcpyHostToDevice, rt->stream));
+  } else {
+    // Dense host rows -> padded device rows.  A strided cudaMemcpy2D of 2.4 KB rows runs at
+    // ~17 GB/s; contiguous chunks into a staging buffer run at PCIe speed and the re-pitch
+    // is a device copy at HBM speed (r1 run 4: 10.1 GB upload 600 ms -> ~190 ms).
+    const int64_t chunkRows = std::max<int64_t>(1, (int64_t)(64u << 20) / x.H);   // ~256 MB of floats
+    rt->ensure_staging((size_t)std::min<int64_t>(chunkRows, x.rows) * x.H * sizeof(float));
+    const float* h = static_cast<const float*>(host);
+    for (int64_t r0 = 0; r0 < x.rows; r0 += chunkRows) {
+      const int64_t nr = std::min<int64_t>(chunkRows, x.rows - r0);
+      ROC_CHECK(cudaMemcpyAsync(rt->staging, h + r0 * x.H, (size_t)nr * x.H * 4, cudaMemcpyHostToDevice, rt->stream));
+      ROC_CHECK(roc_copy2d(nr, x.H, (const float*)rt->staging, x.H, dst + r0 * x.ld, x.ld, rt->stream));
+    }
+  }
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
 }
 

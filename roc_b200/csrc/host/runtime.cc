@@ -80,6 +80,12 @@ void RuntimeImpl::sg_end() {
   ROC_CHECK(cudaEventRecord(sgTimings.back().b, stream));
 }
 
+void RuntimeImpl::ensure_staging(size_t bytes) {
+  if (bytes <= stagingBytes) return;
+  staging = dmalloc(bytes);
+  stagingBytes = bytes;
+}
+
 void RuntimeImpl::ensure_lin_ws(size_t bytes) {
   if (bytes <= linWsBytes) return;
   linWs = dmalloc(bytes);

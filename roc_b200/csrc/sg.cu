@@ -27,6 +27,7 @@
 // Algorithmic bytes per launch: E*(4H+4) + Nloc*(4H+8).
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <cstdlib>
 #include <new>
 #include "common.cuh"
 
@@ -133,12 +134,22 @@ struct SgParams {
   uint32_t Q;          // valid T-columns per row
   uint32_t E, numChunks, numHeavy;
   int epi;
+  int dense;           // mean degree >= chunk size: nearly every row is cut at chunk boundaries
 };
+
+// out[v] = relu?(acc / sqrtf(deg)) — what the model applies right after
+// scatter_gather (gnn.cc:84-85), IEEE sqrt and divide like graphnorm_kernel.cu:49-51.
+template <int VEC>
+__device__ __noinline__ void epi_store(typename V<VEC>::T v, typename V<VEC>::T* dst, uint32_t deg, int epi) {
+  if (epi & ROC_SG_EPI_NORM) v = V<VEC>::div(v, sqrtf((float)deg));
+  if (epi & ROC_SG_EPI_RELU) v = V<VEC>::relu(v);
+  V<VEC>::st(dst, v);
+}
 
 // ------------------------------------------------------------- main kernel ---
 // One worker (L lanes) per chunk.  Lane `lane` owns T-columns lane + ch*L.
-template <int VEC, int L, int NCH, int U>
-__global__ void __launch_bounds__(SG_THREADS)
+template <int VEC, int L, int NCH, int U, int MINB>
+__global__ void __launch_bounds__(SG_THREADS, MINB)
 sg_chunk_kernel(const SgParams p) {
   typedef typename V<VEC>::T T;
   constexpr int WPB = SG_THREADS / L;
@@ -196,28 +207,22 @@ sg_chunk_kernel(const SgParams p) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
 
+  // Row store.  The epilogue (IEEE sqrt + divides) lives in ONE out-of-line copy:
+  // inlining it at every edge position made the kernel 4096 SASS instructions and
+  // instruction-fetch bound (ncu: stalled_no_instruction 22.9 per issue, r1 run 2).
   auto flush = [&]() {
-    if (kind == 0) {
-      T* dst = reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC;
+    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
+                         : out + (size_t)cur * p.ldOut;
+    dst += lane;
+    const int epi = (kind == 1) ? p.epi : 0;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ch++) if (act[ch]) V<VEC>::st(dst + lane + ch * L, acc[ch]);
-    } else {
-      T* dst = out + (size_t)cur * p.ldOut;
-      const bool fin = (kind == 1);
-      float d = 1.0f;
-      if (fin && (p.epi & ROC_SG_EPI_NORM)) d = sqrtf((float)(curT - curS));
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        if (act[ch]) {
-          T v = acc[ch];
-          if (fin && (p.epi & ROC_SG_EPI_NORM)) v = V<VEC>::div(v, d);
-          if (fin && (p.epi & ROC_SG_EPI_RELU)) v = V<VEC>::relu(v);
-          V<VEC>::st(dst + lane + ch * L, v);
-        }
+    for (int ch = 0; ch < NCH; ch++) {
+      if (act[ch]) {
+        if (epi) epi_store<VEC>(acc[ch], dst + ch * L, curT - curS, epi);
+        else V<VEC>::st(dst + ch * L, acc[ch]);
       }
+      acc[ch] = V<VEC>::zero();
     }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
   };
   auto advance = [&]() {  // move to the next owned row
     cur += 1; curS = curT; curT = rs[cur + 1];
@@ -226,22 +231,19 @@ sg_chunk_kernel(const SgParams p) {
     kind = heavy ? 2 : 1;
   };
 
-  for (uint32_t base = e; base < ee; base += 32) {
-    uint32_t idx[32 / L];
-#pragma unroll
-    for (int j = 0; j < 32 / L; j++) {
-      uint32_t k = base + j * L + lane;
-      idx[j] = (k < ee) ? __ldg(col + k) : 0u;
-    }
-#pragma unroll
-    for (int g = 0; g < 32; g += U) {
-      if (base + g >= ee) break;  // worker-uniform
+  // L source ids per batch, one per lane, the next batch prefetched before the gathers
+  uint32_t idx = (e + lane < ee) ? __ldg(col + e + lane) : 0u;
+  for (uint32_t base = e; base < ee; base += L) {
+    const uint32_t cnt = min((uint32_t)L, ee - base);
+    const uint32_t nk = base + L + lane;
+    const uint32_t nextIdx = (nk < ee) ? __ldg(col + nk) : 0u;
+#pragma unroll 1
+    for (uint32_t g = 0; g < cnt; g += U) {
       T v[U][NCH];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int k = g + u;
-        uint32_t src = __shfl_sync(wmask, idx[k / L], k % L, L);
-        const bool ok = base + k < ee;
+        const uint32_t src = __shfl_sync(wmask, idx, g + u, L);
+        const bool ok = g + u < cnt;
         const T* rowp = in + (size_t)src * p.ldIn + lane;
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
@@ -249,17 +251,117 @@ sg_chunk_kernel(const SgParams p) {
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const uint32_t ecur = base + g + u;
-        if (ecur < ee) {
+        if (g + u < cnt) {
+          const uint32_t ecur = base + g + u;
           while (ecur == segEnd) { flush(); advance(); }
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
         }
       }
     }
+    idx = nextIdx;
   }
   flush();
   while (cur + 1 < r1) { advance(); flush(); }  // trailing zero-degree rows
+}
+
+// ------------------------------------------------- main kernel, variant S ---
+// Same schedule and results as sg_chunk_kernel, different loop shape: each
+// iteration gathers the next n = min(U, edges left in this row segment, edges
+// left in the index batch) rows and adds them without per-edge boundary tests, so
+// the row store appears once in the code (smallest instruction footprint).
+template <int VEC, int L, int NCH, int U, int MINB>
+__global__ void __launch_bounds__(SG_THREADS, MINB)
+sg_chunk_kernel_s(const SgParams p) {
+  typedef typename V<VEC>::T T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  const int lane = threadIdx.x % L;
+  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
+  if (w >= p.numChunks) return;
+  const unsigned wmask = (L == 32) ? 0xffffffffu
+                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t* __restrict__ col = p.col;
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in) + lane;
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+
+  const uint32_t cb = w * CH;
+  const uint32_t ce = min(cb + CH, p.E);
+  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
+  uint32_t cur, curS, curT, segEnd, e;
+  int kind;
+  bool carryIn = false;
+  if (r0 > 0) {
+    uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true;
+      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) return;
+    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
+
+  uint32_t base = e;                                   // first edge of the index batch held in `idx`
+  uint32_t idx = (base + lane < p.E) ? __ldg(col + base + lane) : 0u;
+  for (;;) {
+    // ---- add the rest of this segment
+    while (e < segEnd) {
+      if (e >= base + L) {                              // refill the index batch
+        base = e;
+        idx = (base + lane < p.E) ? __ldg(col + base + lane) : 0u;
+      }
+      const uint32_t off = e - base;
+      const uint32_t n = min(min((uint32_t)U, segEnd - e), (uint32_t)L - off);
+      T v[U][NCH];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t src = __shfl_sync(wmask, idx, off + u, L);
+        const bool ok = (uint32_t)u < n;
+        const T* rowp = in + (size_t)src * p.ldIn;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+          v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+      e += n;
+    }
+    // ---- store the segment (the only store site)
+    {
+      T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
+                           : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
+      dst += lane;
+      const int epi = (kind == 1) ? p.epi : 0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) {
+        if (act[ch]) {
+          if (epi) epi_store<VEC>(acc[ch], dst + ch * L, curT - curS, epi);
+          else V<VEC>::st(dst + ch * L, acc[ch]);
+        }
+        acc[ch] = V<VEC>::zero();
+      }
+    }
+    // ---- next owned row, if any
+    cur += 1;
+    if (cur >= r1) break;
+    curS = curT; curT = rs[cur + 1];
+    const bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
 }
 
 // ----------------------------------------------------------- fix-up kernel ---
@@ -301,25 +403,30 @@ sg_fixup_kernel(const SgParams p) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
   }
-  float d = 1.0f;
-  if (p.epi & ROC_SG_EPI_NORM) d = sqrtf((float)(t - s));
 #pragma unroll
-  for (int ch = 0; ch < NCH; ch++) {
-    if (act[ch]) {
-      T v = acc[ch];
-      if (p.epi & ROC_SG_EPI_NORM) v = V<VEC>::div(v, d);
-      if (p.epi & ROC_SG_EPI_RELU) v = V<VEC>::relu(v);
-      V<VEC>::st(dst + lane + ch * L, v);
-    }
-  }
+  for (int ch = 0; ch < NCH; ch++)
+    if (act[ch]) epi_store<VEC>(acc[ch], dst + lane + ch * L, t - s, p.epi);
 }
 
-template <int VEC, int L, int NCH, int U>
+// Loop shape: A (per-edge row test, gathers overlap across short rows) wins on
+// sparse graphs with narrow rows, S (one store site) on wide rows and on dense
+// graphs where almost every row spans chunks (r1 run 3: R-MAT-22 H=16 1.42 vs 2.05 ms,
+// H=256 10.9 vs 9.9 ms; Reddit-shaped H=64 3.68 vs 3.18 ms).  ROC_SG_VARIANT=a|s forces one.
+static int sg_variant_env() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'a' ? 0 : 1); }
+  return v;
+}
+
+template <int VEC, int L, int NCH, int U, int MINB>
 static int launch_cfg(const SgParams& p, cudaStream_t st) {
   constexpr int WPB = SG_THREADS / L;
   if (p.numChunks) {
     unsigned grid = (p.numChunks + WPB - 1) / WPB;
-    sg_chunk_kernel<VEC, L, NCH, U><<<grid, SG_THREADS, 0, st>>>(p);
+    int variant = sg_variant_env();
+    if (variant < 0) variant = (L == 32 || p.dense) ? 1 : 0;
+    if (variant == 0) sg_chunk_kernel<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
+    else sg_chunk_kernel_s<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
     ROC_LAUNCH_CHECK();
   }
   if (p.numHeavy) {
@@ -333,13 +440,13 @@ static int launch_cfg(const SgParams& p, cudaStream_t st) {
 template <int VEC>
 static int dispatch(const SgParams& p, cudaStream_t st) {
   const uint32_t Q = p.Q;
-  if (Q <= 4) return launch_cfg<VEC, 4, 1, 8>(p, st);
-  if (Q <= 8) return launch_cfg<VEC, 8, 1, 8>(p, st);
-  if (Q <= 16) return launch_cfg<VEC, 16, 1, 8>(p, st);
-  if (Q <= 32) return launch_cfg<VEC, 32, 1, 8>(p, st);
-  if (Q <= 64) return launch_cfg<VEC, 32, 2, 4>(p, st);
-  if (Q <= 128) return launch_cfg<VEC, 32, 4, 2>(p, st);
-  if (Q <= 256) return launch_cfg<VEC, 32, 8, 1>(p, st);
+  if (Q <= 4) return launch_cfg<VEC, 4, 1, 4, 4>(p, st);
+  if (Q <= 8) return launch_cfg<VEC, 8, 1, 8, 4>(p, st);
+  if (Q <= 16) return launch_cfg<VEC, 16, 1, 8, 4>(p, st);
+  if (Q <= 32) return launch_cfg<VEC, 32, 1, 8, 4>(p, st);
+  if (Q <= 64) return launch_cfg<VEC, 32, 2, 4, 3>(p, st);
+  if (Q <= 128) return launch_cfg<VEC, 32, 4, 2, 3>(p, st);
+  if (Q <= 256) return launch_cfg<VEC, 32, 8, 1, 2>(p, st);
   return ROC_ERR_UNSUPPORTED;
 }
 
@@ -461,6 +568,7 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
     p.rs = pl->rs; p.firstRow = pl->firstRow; p.carryIdx = pl->carryIdx; p.heavyRows = pl->heavyRows;
     p.col = pl->col; p.in = in + c0; p.out = out + c0; p.carry = pl->carry;
     p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.epi = epilogue;
+    p.dense = (pl->nloc > 0 && pl->E / pl->nloc >= (uint32_t)SG_CH) ? 1 : 0;
     int rc;
     if (vec) {
       p.ldIn = (size_t)ldIn / 4; p.ldOut = (size_t)ldOut / 4; p.ldC = pl->carryLd / 4;

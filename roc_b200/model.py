@@ -226,6 +226,7 @@ def build_gcn(model, layers, dropout_rate, lr=0.01, weight_decay=0.05):
     label = model.create_node_tensor(layers[-1])
     mask = model.create_node_tensor(1, is_int=True)
     t = x
+    relu_outs = []
     for i in range(1, L):
         t = model.dropout(t, dropout_rate)
         skip = t
@@ -235,10 +236,11 @@ def build_gcn(model, layers, dropout_rate, lr=0.01, weight_decay=0.05):
         t = model.indegree_norm(t)
         if i != L - 1:
             t = model.relu(t)
+            relu_outs.append(t)
         if L > 3:   # residual branch, gnn.cc:86-90
             skip = model.linear(skip, layers[i], _lib.AC_MODE_NONE)
             t = model.add(t, skip)
     model.softmax_cross_entropy(t, label, mask)
     model.adam(lr, weight_decay)
     model.init()
-    return {"input": x, "label": label, "mask": mask, "logits": t}
+    return {"input": x, "label": label, "mask": mask, "logits": t, "relu_outs": relu_outs}

@@ -36,11 +36,12 @@ def run_product(row_end, col, feats, labels, mask, layers, dropout, epochs, fuse
     m.set_labels(h["label"], labels)
     m.set_tensor(h["mask"], mask.astype(np.int32))
     w0 = [m.get_parameter(p) for p in range(m.num_parameters())]
-    out = {"w0": w0, "perf": [], "logits": None, "dW": None}
+    out = {"w0": w0, "perf": [], "logits": None, "dW": None, "relu_masks": []}
     for ep in range(epochs):
         m.train_mode()
         m.zero_gradients()
         m.forward()
+        out["relu_masks"].append([m.get_tensor(t) > 0 for t in h["relu_outs"]])
         if ep == 0:
             out["logits"] = m.get_tensor(h["logits"])
         m.backward()
@@ -56,12 +57,31 @@ def run_product(row_end, col, feats, labels, mask, layers, dropout, epochs, fuse
     return out
 
 
-def run_oracle(row_end, col, feats, labels, mask, layers, dropout, epochs, w0, lr=0.01, wd=0.05):
+def sync_relu_masks(o, masks):
+    """ReLU at a pre-activation within rounding of 0 is ill-conditioned: the product (fp32 / 3xTF32 sums)
+    and the oracle (fp64 sums) may legitimately disagree on its sign, which changes a whole dW row.  Masks
+    may differ ONLY there (|pre| <= 1e-4 * max|pre|, the parity tolerance); where they do, the oracle's
+    backward uses the product's mask so the gradients stay comparable."""
+    recs = [r for r in o.saved if r["relu"]]
+    assert len(recs) == len(masks)
+    for rec, pm in zip(recs, masks):
+        om = rec["a"] > 0
+        diff = pm != om
+        if diff.any():
+            pre = rec["pre"]
+            assert np.abs(pre[diff]).max() <= 1e-4 * np.abs(pre).max(), "relu masks differ away from zero"
+            rec["a_override"] = pm.astype(np.float32)
+    return int(sum((pm != (r["a"] > 0)).sum() for r, pm in zip(recs, masks)))
+
+
+def run_oracle(row_end, col, feats, labels, mask, layers, dropout, epochs, w0, lr=0.01, wd=0.05, relu_masks=None):
     o = oracle.GcnOracle(row_end, col, layers, w0, lr=lr, weight_decay=wd, dropout=dropout)
     oh = datasets.onehot(labels, layers[-1])
-    res = {"perf": []}
+    res = {"perf": [], "flips": 0}
     for ep in range(epochs):
         o.forward(feats, train=True)
+        if relu_masks is not None:
+            res["flips"] += sync_relu_masks(o, relu_masks[ep])
         if ep == 0:
             res["logits"] = o.logits.copy()
         o.backward(oh, mask)
@@ -82,7 +102,8 @@ def test_gcn_training_matches_oracle(layers, dropout, fuse):
     case = make_case(layers=layers)
     epochs = 4
     got = run_product(*case, layers, dropout, epochs, fuse)
-    want = run_oracle(*case, layers, dropout, epochs, got["w0"])
+    want = run_oracle(*case, layers, dropout, epochs, got["w0"], relu_masks=got["relu_masks"])
+    assert want["flips"] <= 4, "too many relu sign disagreements: %d" % want["flips"]
     rel_close(got["logits"], want["logits"], what="logits epoch 0")
     for p, (a, b) in enumerate(zip(got["dW"], want["dW"])):
         rel_close(a, b, rtol=2e-4, what="dW[%d] epoch 0" % p)
