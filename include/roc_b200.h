@@ -18,7 +18,9 @@
  *  - node tensors are row-major [rows][ld] fp32 with `ld >= H` floats between
  *    rows (the reference's layout is ld == H, gnn.cc:480-486).  The vectorised
  *    paths need ld % 4 == 0 and 16-byte aligned bases; other shapes take a
- *    scalar path.  Columns H..ld-1 are never read or written;
+ *    scalar path.  Pad columns H..ld-1 may be read and rewritten by the
+ *    vectorised paths (whole float4s) but never influence columns < H; the host
+ *    keeps them zero;
  *  - graph ids follow types.h:5-15: V_ID = uint32, E_ID = uint64;
  *    rowEnd[v-rowLeft] is the GLOBAL END offset of v's in-edge list
  *    (NodeStruct.index, load_task.cu:283-288), the first local row starts at
@@ -242,6 +244,12 @@ int roc_scale(int64_t count, float a, float b, float* W, roc_stream_t stream);
 /* Replaces assign_kernel, cuda_helper.cu:11-18 (zero_grad_task_impl,
  * ZerosInitializer): 2-D fill of the [rows][H] window of a [rows][ld] tensor. */
 int roc_fill(int64_t rows, int H, float value, float* x, int64_t ld, roc_stream_t stream);
+/* Test hook: the fused indegree_norm epilogues divide by a row-uniform sqrtf(deg) with a shared
+ * reciprocal + FMA correction instead of one div.rn per element.  Counts, over the `count` fp32 bit
+ * patterns starting at firstBits, how many results differ from `x / d` (must be 0; NaN == NaN).
+ * *d_mismatches (device u64) is accumulated into. */
+int roc_selftest_rowdiv(float d, uint64_t firstBits, uint64_t count, uint64_t* d_mismatches,
+                        roc_stream_t stream);
 /* Replaces copy_kernel, cuda_helper.cu:20-27 (dropout's infer path, staging): 2-D copy of
  * the [rows][H] window between tensors of different leading dimensions. */
 int roc_copy2d(int64_t rows, int H, const float* src, int64_t ldSrc, float* dst, int64_t ldDst,

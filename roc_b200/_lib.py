@@ -75,6 +75,7 @@ PROTOTYPES = {
     "roc_scale": (i32, [i64, f32, f32, vp, vp]),
     "roc_fill": (i32, [i64, i32, f32, vp, i64, vp]),
     "roc_copy2d": (i32, [i64, i32, vp, i64, vp, i64, vp]),
+    "roc_selftest_rowdiv": (i32, [f32, u64, u64, vp, vp]),
     # ---- roc_host.h
     "roc_host_create": (vp, [i32, i32, i32]),
     "roc_host_destroy": (None, [vp]),

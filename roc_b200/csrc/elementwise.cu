@@ -56,12 +56,17 @@ k_norm(int64_t rows, int Wq, uint64_t colLeft, const uint64_t* __restrict__ rowE
         v.x = (y.x > 0.f) ? v.x : 0.f; v.y = (y.y > 0.f) ? v.y : 0.f;
         v.z = (y.z > 0.f) ? v.z : 0.f; v.w = (y.w > 0.f) ? v.w : 0.f;
       }
-      v.x /= d; v.y /= d; v.z /= d; v.w /= d;
+      // zero numerators skip the divide (they would take div.rn's slow path; 0/d == 0 for d != 0)
+      const bool dz = (d == 0.0f);
+      if (v.x != 0.f || dz) v.x /= d;
+      if (v.y != 0.f || dz) v.y /= d;
+      if (v.z != 0.f || dz) v.z /= d;
+      if (v.w != 0.f || dz) v.w /= d;
       *reinterpret_cast<float4*>(out + r * ldOut + 4 * c) = v;
     } else {
       float v = in[r * ldIn + c];
       if (reluOf) v = (reluOf[r * ldR + c] > 0.f) ? v : 0.f;
-      out[r * ldOut + c] = v / d;
+      out[r * ldOut + c] = (v != 0.f || d == 0.0f) ? v / d : v;
     }
   }
 }
@@ -261,6 +266,114 @@ k_softmax_xent(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
   }
 }
 
+// Narrow-row version (C <= 4*LR): LR lanes per row, each lane keeps its (up to 4)
+// logits in registers, so expf runs once per element and a warp handles 32/LR rows.
+// Same arithmetic as k_softmax_xent (max, exp, sum, divide; first-max argmax).
+template <bool ONEHOT, int LR>
+__global__ void __launch_bounds__(256)
+k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
+                      const float* __restrict__ onehot, int64_t ldl, const int32_t* __restrict__ labelIdx,
+                      const int32_t* __restrict__ mask, float* __restrict__ g, int64_t ldg,
+                      roc_perf_metrics* perf) {
+  __shared__ float sLoss;
+  __shared__ int sCnt[6];
+  if (threadIdx.x == 0) sLoss = 0.f;
+  if (threadIdx.x < 6) sCnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lr = threadIdx.x % LR;
+  const unsigned gmask = (LR == 32) ? 0xffffffffu : (((1u << LR) - 1u) << (((threadIdx.x & 31) / LR) * LR));
+  const int rowsPerBlock = blockDim.x / LR;
+  float myLoss = 0.f;
+  int cnt[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t r = blockIdx.x * (int64_t)rowsPerBlock + threadIdx.x / LR; r < rows;
+       r += (int64_t)gridDim.x * rowsPerBlock) {
+    const float* zr = z + r * ldz;
+    float v[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = lr + j * LR;
+      v[j] = (c < C) ? zr[c] : -INFINITY;
+      m = fmaxf(m, v[j]);
+    }
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o, LR));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = lr + j * LR;
+      v[j] = (c < C) ? expf(v[j] - m) : 0.f;
+      sum += v[j];
+    }
+    // same summation tree for every row => deterministic; order differs from a serial loop (within 1e-4)
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o, LR);
+    const int mk = mask[r];
+    const int tl = ONEHOT ? -1 : labelIdx[r];
+    float best = 0.0f; int bestIdx = -1; int trueIdx = -1; float pTrue = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = lr + j * LR;
+      if (c < C) {
+        const float p = v[j] / sum;
+        if (p > best) { best = p; bestIdx = c; }
+        float lab;
+        if (ONEHOT) { lab = onehot[r * ldl + c]; if (lab > 0.5f) trueIdx = c; }
+        else { lab = (c == tl) ? 1.0f : 0.0f; if (c == tl) trueIdx = c; }
+        if (trueIdx == c) pTrue = p;
+        g[r * ldg + c] = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int o = LR / 2; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(gmask, best, o, LR);
+      int oi = __shfl_xor_sync(gmask, bestIdx, o, LR);
+      if (ob > best || (ob == best && oi >= 0 && (bestIdx < 0 || oi < bestIdx))) { best = ob; bestIdx = oi; }
+      int ot = __shfl_xor_sync(gmask, trueIdx, o, LR);
+      float op = __shfl_xor_sync(gmask, pTrue, o, LR);
+      if (ot > trueIdx) { trueIdx = ot; pTrue = op; }
+    }
+    if (lr == 0) {
+      const bool ok = (trueIdx == bestIdx);
+      if (mk == ROC_MASK_TRAIN) { myLoss += 1.0f - pTrue; cnt[0]++; if (ok) cnt[3]++; }
+      else if (mk == ROC_MASK_VAL) { cnt[2]++; if (ok) cnt[5]++; }
+      else if (mk == ROC_MASK_TEST) { cnt[1]++; if (ok) cnt[4]++; }
+    }
+  }
+  if (perf) {
+    if (lr == 0) {
+      if (myLoss != 0.f) atomicAdd(&sLoss, myLoss);
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (cnt[k]) atomicAdd(&sCnt[k], cnt[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (sLoss != 0.f) atomicAdd(&perf->trainLoss, sLoss);
+      if (sCnt[0]) atomicAdd(&perf->trainAll, sCnt[0]);
+      if (sCnt[1]) atomicAdd(&perf->testAll, sCnt[1]);
+      if (sCnt[2]) atomicAdd(&perf->valAll, sCnt[2]);
+      if (sCnt[3]) atomicAdd(&perf->trainCorrect, sCnt[3]);
+      if (sCnt[4]) atomicAdd(&perf->testCorrect, sCnt[4]);
+      if (sCnt[5]) atomicAdd(&perf->valCorrect, sCnt[5]);
+    }
+  }
+}
+
+template <bool ONEHOT>
+static void launch_softmax(int64_t rows, int C, const float* logits, int64_t ldZ, const float* labels, int64_t ldL,
+                           const int32_t* labelIdx, const int32_t* mask, float* grad, int64_t ldG,
+                           roc_perf_metrics* perf, cudaStream_t st) {
+  if (C <= 32) {
+    k_softmax_xent_narrow<ONEHOT, 8><<<ew_grid(rows * 8, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+  } else if (C <= 64) {
+    k_softmax_xent_narrow<ONEHOT, 16><<<ew_grid(rows * 16, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+  } else if (C <= 128) {
+    k_softmax_xent_narrow<ONEHOT, 32><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+  } else {
+    k_softmax_xent<ONEHOT><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+  }
+}
+
 // ------------------------------------------------------------------ adam -----
 __global__ void __launch_bounds__(EW_T)
 k_adam(int64_t count, float alpha_t, float beta1, float beta2, float wd, float eps,
@@ -409,8 +522,10 @@ extern "C" int roc_indegree_norm(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_
   // a fused relu mask shares the output's leading dimension convention: it is the
   // forward output tensor, same shape as `in`
   int64_t ldR = ldIn;
-  if (vec_ok(H, {ldIn, ldOut}, {in, out, reluOf})) {
-    k_norm<4><<<ew_grid(rows * (H / 4), EW_T), EW_T, 0, st>>>(rows, H / 4, colLeft, rowEnd, in, ldIn, out, ldOut, reluOf, ldR);
+  // padded rows (ld % 4 == 0): whole float4s, the pad columns ride along (0 / d stays 0)
+  if (vec_ok(4, {ldIn, ldOut}, {in, out, reluOf})) {
+    const int Wq = (H + 3) / 4;
+    k_norm<4><<<ew_grid(rows * Wq, EW_T), EW_T, 0, st>>>(rows, Wq, colLeft, rowEnd, in, ldIn, out, ldOut, reluOf, ldR);
   } else {
     k_norm<1><<<ew_grid(rows * H, EW_T), EW_T, 0, st>>>(rows, H, colLeft, rowEnd, in, ldIn, out, ldOut, reluOf, ldR);
   }
@@ -502,8 +617,7 @@ extern "C" int roc_softmax_xent_bwd(int64_t rows, int C, const float* logits, in
                                     roc_perf_metrics* perf, roc_stream_t stream) {
   if (!logits || !labels || !mask || !grad || rows < 0 || C <= 0 || ldZ < C || ldL < C || ldG < C) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
-  unsigned grid = ew_grid(rows * 32, 256);
-  k_softmax_xent<true><<<grid, 256, 0, as_stream(stream)>>>(rows, C, logits, ldZ, labels, ldL, nullptr, mask, grad, ldG, perf);
+  launch_softmax<true>(rows, C, logits, ldZ, labels, ldL, nullptr, mask, grad, ldG, perf, as_stream(stream));
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }
@@ -515,8 +629,7 @@ extern "C" int roc_softmax_xent_bwd_idx(int64_t rows, int C, const float* logits
                                         roc_perf_metrics* perf, roc_stream_t stream) {
   if (!logits || !labelIdx || !mask || !grad || rows < 0 || C <= 0 || ldZ < C || ldG < C) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
-  unsigned grid = ew_grid(rows * 32, 256);
-  k_softmax_xent<false><<<grid, 256, 0, as_stream(stream)>>>(rows, C, logits, ldZ, nullptr, 0, labelIdx, mask, grad, ldG, perf);
+  launch_softmax<false>(rows, C, logits, ldZ, nullptr, 0, labelIdx, mask, grad, ldG, perf, as_stream(stream));
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }
@@ -534,6 +647,29 @@ extern "C" int roc_scale(int64_t count, float a, float b, float* W, roc_stream_t
   if (!W || count < 0) return ROC_ERR_INVALID;
   if (count == 0) return ROC_OK;
   k_scale<<<ew_grid(count, EW_T), EW_T, 0, as_stream(stream)>>>(count, a, b, W);
+  ROC_LAUNCH_CHECK();
+  return ROC_OK;
+}
+
+// exhaustive check of the row-uniform division against div.rn (test hook)
+__global__ void __launch_bounds__(256)
+k_selftest_rowdiv(float d, uint64_t firstBits, uint64_t count, unsigned long long* mismatches) {
+  const roc::RowDiv rd = roc::rowdiv_make(d);
+  unsigned long long bad = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float((uint32_t)(firstBits + i));
+    const float want = a / d;
+    const float got = roc::rowdiv(a, rd);
+    if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got)) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int roc_selftest_rowdiv(float d, uint64_t firstBits, uint64_t count, uint64_t* d_mismatches,
+                                   roc_stream_t stream) {
+  if (!d_mismatches) return ROC_ERR_INVALID;
+  k_selftest_rowdiv<<<sm_count() * 8, 256, 0, as_stream(stream)>>>(d, firstBits, count,
+                                                                 reinterpret_cast<unsigned long long*>(d_mismatches));
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }

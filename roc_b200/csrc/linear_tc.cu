@@ -159,6 +159,7 @@ k_tc_linear_fwd(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         uint64_t st = (row == 0) ? p.colLeft : p.rowEnd[row - 1];
         d = sqrtf((float)(uint32_t)(p.rowEnd[row] - st));
       }
+      const RowDiv rd = rowdiv_make(d);
       const uint32_t taddr = tmemBase + ((uint32_t)((warp - 4) * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t r[16];
@@ -173,7 +174,7 @@ k_tc_linear_fwd(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             for (int k = 0; k < 4; k++) {
               float x = __uint_as_float(r[q * 4 + k]);
               if (p.relu) x = relu_nanprop(x);
-              if (p.rowEnd) x = x / d;
+              if (p.rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
               v[k] = x;
             }
             const int c = c0 + q * 4;

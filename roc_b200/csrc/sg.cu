@@ -105,7 +105,17 @@ template <> struct V<4> {
   static __device__ __forceinline__ T ld_plain(const T* p) { return *p; }
   static __device__ __forceinline__ void st(T* p, const T& v) { *p = v; }
   static __device__ __forceinline__ void add(T& a, const T& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-  static __device__ __forceinline__ T div(const T& a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+  // IEEE divide.  A zero numerator sends nvcc's div.rn sequence down its slow path (FCHK flags
+  // zero operands) and one such lane drags the whole warp along: gradients and pad columns are
+  // full of zeros (+28 % instructions in the backward launches, r1 run 12).  0/d == 0 (same
+  // sign) for d != 0, so those lanes skip the divide; d == 0 (degree 0) still yields NaN/Inf.
+  static __device__ __forceinline__ float div1(float a, float d) { return (a != 0.0f || d == 0.0f) ? a / d : a; }
+  static __device__ __forceinline__ T div(const T& a, float d) {
+    return make_float4(div1(a.x, d), div1(a.y, d), div1(a.z, d), div1(a.w, d));
+  }
+  static __device__ __forceinline__ T rdiv(const T& a, const RowDiv& r) {
+    return make_float4(rowdiv(a.x, r), rowdiv(a.y, r), rowdiv(a.z, r), rowdiv(a.w, r));
+  }
   static __device__ __forceinline__ T relu(const T& a) {
     return make_float4(relu_nanprop(a.x), relu_nanprop(a.y), relu_nanprop(a.z), relu_nanprop(a.w));
   }
@@ -117,7 +127,8 @@ template <> struct V<1> {
   static __device__ __forceinline__ T ld_plain(const T* p) { return *p; }
   static __device__ __forceinline__ void st(T* p, const T& v) { *p = v; }
   static __device__ __forceinline__ void add(T& a, const T& b) { a += b; }
-  static __device__ __forceinline__ T div(const T& a, float d) { return a / d; }
+  static __device__ __forceinline__ T div(const T& a, float d) { return (a != 0.0f || d == 0.0f) ? a / d : a; }
+  static __device__ __forceinline__ T rdiv(const T& a, const RowDiv& r) { return rowdiv(a, r); }
   static __device__ __forceinline__ T relu(const T& a) { return relu_nanprop(a); }
 };
 
@@ -139,9 +150,15 @@ struct SgParams {
 
 // out[v] = relu?(acc / sqrtf(deg)) — what the model applies right after
 // scatter_gather (gnn.cc:84-85), IEEE sqrt and divide like graphnorm_kernel.cu:49-51.
+// The divisor is uniform over the row, so the divide is the row-uniform form of common.cuh
+// (one refined reciprocal, 3 FMAs per element, bit-identical to div.rn): the plain `/` here
+// cost +0.7 ms (H=64) .. +1.8 ms (H=41, zero pad lanes on the slow path) per launch (r1 run 14).
 template <int VEC>
-__device__ __noinline__ void epi_store(typename V<VEC>::T v, typename V<VEC>::T* dst, uint32_t deg, int epi) {
-  if (epi & ROC_SG_EPI_NORM) v = V<VEC>::div(v, sqrtf((float)deg));
+__device__ __forceinline__ void epi_store(typename V<VEC>::T v, typename V<VEC>::T* dst, uint32_t deg, int epi) {
+  if (epi & ROC_SG_EPI_NORM) {
+    const RowDiv rd = rowdiv_make(sqrtf((float)deg));
+    v = V<VEC>::rdiv(v, rd);
+  }
   if (epi & ROC_SG_EPI_RELU) v = V<VEC>::relu(v);
   V<VEC>::st(dst, v);
 }
@@ -231,35 +248,41 @@ sg_chunk_kernel(const SgParams p) {
     kind = heavy ? 2 : 1;
   };
 
-  // L source ids per batch, one per lane, the next batch prefetched before the gathers
-  uint32_t idx = (e + lane < ee) ? __ldg(col + e + lane) : 0u;
-  for (uint32_t base = e; base < ee; base += L) {
-    const uint32_t cnt = min((uint32_t)L, ee - base);
-    const uint32_t nk = base + L + lane;
-    const uint32_t nextIdx = (nk < ee) ? __ldg(col + nk) : 0u;
+  // Every lane reads the source ids itself (same address across the worker: one broadcast
+  // transaction from L1); sub-warp shuffles with a runtime mask cost a MATCH.ANY sequence each.
+  (void)wmask;
 #pragma unroll 1
-    for (uint32_t g = 0; g < cnt; g += U) {
-      T v[U][NCH];
+  for (uint32_t base = e; base < ee; base += U) {
+    const uint32_t cnt = min((uint32_t)U, ee - base);
+    uint32_t srcs[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) srcs[u] = ((uint32_t)u < cnt) ? __ldg(col + base + u) : 0u;
+    T v[U][NCH];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const bool ok = (uint32_t)u < cnt;
+      const T* rowp = in + (size_t)srcs[u] * p.ldIn + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++)
+        v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
+    }
+    if (segEnd - base >= (uint32_t)U) {
+      // all U edges belong to the current row segment: no boundary tests
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+    } else {
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const uint32_t src = __shfl_sync(wmask, idx, g + u, L);
-        const bool ok = g + u < cnt;
-        const T* rowp = in + (size_t)src * p.ldIn + lane;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++)
-          v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (g + u < cnt) {
-          const uint32_t ecur = base + g + u;
+        if ((uint32_t)u < cnt) {
+          const uint32_t ecur = base + u;
           while (ecur == segEnd) { flush(); advance(); }
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
         }
       }
     }
-    idx = nextIdx;
   }
   flush();
   while (cur + 1 < r1) { advance(); flush(); }  // trailing zero-degree rows
@@ -364,6 +387,327 @@ sg_chunk_kernel_s(const SgParams p) {
   }
 }
 
+// ------------------------------------------------- main kernel, variant C ---
+// Same schedule, same per-row summation order, but the gathered rows are staged in
+// shared memory with cp.async (LDGSTS) instead of registers: every lane copies its
+// own 16 bytes of each neighbour row into a per-worker ring of DEPTH = P*GROUP row
+// slots and later adds exactly the bytes it copied (no cross-lane sharing, so no
+// barrier — only cp.async.wait_group).  Bytes in flight per SM are bounded by the
+// ring (~100 KB per CTA) rather than by the register file, and the per-edge
+// instruction count drops (one LDGSTS + one LDS.128 + 4 FADD per 16-byte column).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int L, int NCH, int GROUP, int P>
+__global__ void __launch_bounds__(SG_THREADS, 3)
+sg_chunk_kernel_c(const SgParams p) {
+  typedef float4 T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  constexpr int DEPTH = GROUP * P;
+  extern __shared__ __align__(16) float4 sg_ring[];
+  const int lane = threadIdx.x % L;
+  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
+  // this lane's column of the worker's ring: slot s, chunk ch -> ring[(s * NCH + ch) * L]
+  float4* ring = sg_ring + (size_t)(threadIdx.x / L) * (DEPTH * NCH * L) + lane;
+  if (w >= p.numChunks) return;
+  const unsigned wmask = (L == 32) ? 0xffffffffu
+                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t* __restrict__ col = p.col;
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in) + lane;
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+
+  const uint32_t cb = w * CH;
+  const uint32_t ce = min(cb + CH, p.E);
+  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
+  uint32_t cur, curS, curT, segEnd, e;
+  int kind;
+  bool carryIn = false;
+  if (r0 > 0) {
+    uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true;
+      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) return;
+    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
+  uint32_t ee;
+  if (r1 > r0) {
+    uint32_t s = rs[r1 - 1], t = rs[r1];
+    ee = (t - s > CH) ? min(t, ce) : t;
+  } else {
+    ee = segEnd;
+  }
+  const uint32_t eb = e;
+  const uint32_t nE = ee - eb;
+  const uint32_t nG = (nE + GROUP - 1) / GROUP;
+
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&]() {
+    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
+                         : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
+    dst += lane;
+    const int epi = (kind == 1) ? p.epi : 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      if (act[ch]) {
+        if (epi) epi_store<4>(acc[ch], dst + ch * L, curT - curS, epi);
+        else *(dst + ch * L) = acc[ch];
+      }
+      acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto advance = [&]() {
+    cur += 1; curS = curT; curT = rs[cur + 1];
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  };
+
+  // issue side: L source ids per batch (one per lane), next batch prefetched
+  uint32_t idx = (eb + lane < ee) ? __ldg(col + eb + lane) : 0u;
+  uint32_t nextIdx = (eb + L + lane < ee) ? __ldg(col + eb + L + lane) : 0u;
+  auto issue = [&](uint32_t gi) {
+    if (gi < nG) {
+      const uint32_t off = gi * GROUP;          // edge offset from eb (groups never straddle a batch: GROUP | L)
+      const uint32_t inb = off & (uint32_t)(L - 1);
+      if (inb == 0 && off > 0) {
+        idx = nextIdx;
+        const uint32_t nk = eb + off + L + lane;
+        nextIdx = (nk < ee) ? __ldg(col + nk) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < GROUP; u++) {
+        const uint32_t k = off + u;
+        if (k < nE) {
+          const uint32_t src = __shfl_sync(wmask, idx, inb + u, L);
+          const T* rowp = in + (size_t)src * p.ldIn;
+          float4* slot = ring + (size_t)(k % DEPTH) * (NCH * L);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++)
+            if (act[ch]) cp_async16(slot + ch * L, rowp + ch * L);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < P; g++) issue((uint32_t)g);
+#pragma unroll 1
+  for (uint32_t g = 0; g < nG; g++) {
+    cp_async_wait<P - 1>();          // group g has landed (at most P-1 younger groups still in flight)
+#pragma unroll
+    for (int u = 0; u < GROUP; u++) {
+      const uint32_t k = g * GROUP + u;
+      if (k < nE) {
+        const uint32_t ecur = eb + k;
+        while (ecur == segEnd) { flush(); advance(); }
+        const float4* slot = ring + (size_t)(k % DEPTH) * (NCH * L);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+          if (act[ch]) {
+            const float4 v = slot[ch * L];
+            acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
+          }
+        }
+      }
+    }
+    issue(g + P);                    // refills exactly the slots consumed above
+  }
+  flush();
+  while (cur + 1 < r1) { advance(); flush(); }
+}
+
+// ------------------------------------------- main kernel, variant C (lean) ---
+// Variant C with the instruction stream trimmed (r1 run 10: the first version issued
+// 34 instructions per edge — generic-address arithmetic and per-edge predicates —
+// and was issue-bound once the latency was hidden): 32-bit shared addresses with
+// immediate slot offsets, whole-group fast paths when the group is complete and no
+// row boundary falls inside it.
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+template <int L, int NCH, int GROUP, int P>
+__global__ void __launch_bounds__(SG_THREADS, 3)
+sg_chunk_kernel_c2(const SgParams p) {
+  typedef float4 T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  constexpr uint32_t ROWB = NCH * L * 16;          // bytes per ring slot
+  constexpr uint32_t GRPB = GROUP * ROWB;          // bytes per group of slots
+  constexpr uint32_t RINGB = P * GRPB;             // bytes per worker ring
+  extern __shared__ __align__(16) float4 sg_ring[];
+  const int lane = threadIdx.x % L;
+  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
+  const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(sg_ring) + (threadIdx.x / L) * RINGB + lane * 16;
+  if (w >= p.numChunks) return;
+  const unsigned wmask = (L == 32) ? 0xffffffffu
+                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t* __restrict__ col = p.col;
+  const char* inB = reinterpret_cast<const char*>(p.in) + lane * 16;
+  const uint32_t strideB = (uint32_t)p.ldIn * 16u;   // bytes between input rows (ldIn is in float4 units)
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+
+  const uint32_t cb = w * CH;
+  const uint32_t ce = min(cb + CH, p.E);
+  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
+  uint32_t cur, curS, curT, segEnd, e;
+  int kind;
+  bool carryIn = false;
+  if (r0 > 0) {
+    uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true;
+      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) return;
+    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
+  uint32_t ee;
+  if (r1 > r0) {
+    uint32_t s = rs[r1 - 1], t = rs[r1];
+    ee = (t - s > CH) ? min(t, ce) : t;
+  } else {
+    ee = segEnd;
+  }
+  const uint32_t eb = e;
+  const uint32_t nE = ee - eb;
+  const uint32_t nG = (nE + GROUP - 1) / GROUP;
+
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&]() {
+    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
+                         : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
+    dst += lane;
+    const int epi = (kind == 1) ? p.epi : 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      if (act[ch]) {
+        if (epi) epi_store<4>(acc[ch], dst + ch * L, curT - curS, epi);
+        else *(dst + ch * L) = acc[ch];
+      }
+      acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto advance = [&]() {
+    cur += 1; curS = curT; curT = rs[cur + 1];
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  };
+
+  // issue group gi into the ring slots at byte offset slotOff (= (gi % P) * GRPB).
+  // Every lane of the worker reads the source id itself (same address: one broadcast
+  // transaction, L1-resident): a sub-warp __shfl_sync with a runtime mask costs a
+  // MATCH.ANY sequence, ~11 instructions per edge (ncu source page, r1 run 11).
+  (void)wmask;
+  auto issue = [&](uint32_t gi, uint32_t slotOff) {
+    if (gi < nG) {
+      const uint32_t off = gi * GROUP;
+      const uint32_t* cp = col + eb + off;
+      const uint32_t sa = ringBase + slotOff;
+      if (off + GROUP <= nE) {
+        uint32_t srcs[GROUP];
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) srcs[u] = __ldg(cp + u);
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) {
+          const char* g = inB + (size_t)srcs[u] * strideB;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++)
+            if (act[ch]) cp_async16_s(sa + u * ROWB + ch * L * 16, g + ch * L * 16);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) {
+          if (off + u < nE) {
+            const uint32_t src = __ldg(cp + u);
+            const char* g = inB + (size_t)src * strideB;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+              if (act[ch]) cp_async16_s(sa + u * ROWB + ch * L * 16, g + ch * L * 16);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (uint32_t g = 0; g < (uint32_t)P; g++) issue(g, g * GRPB);   // one code copy: keep the kernel in the I-cache
+  uint32_t slotOff = 0;
+#pragma unroll 1
+  for (uint32_t g = 0; g < nG; g++) {
+    cp_async_wait<P - 1>();
+    const uint32_t e0 = eb + g * GROUP;
+    const uint32_t sa = ringBase + slotOff;
+    if (segEnd - e0 >= (uint32_t)GROUP) {
+      // the whole group lies inside the current row segment: no boundary tests
+#pragma unroll
+      for (int u = 0; u < GROUP; u++)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+          if (act[ch]) {
+            const float4 v = lds128(sa + u * ROWB + ch * L * 16);
+            acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
+          }
+    } else {
+#pragma unroll
+      for (int u = 0; u < GROUP; u++) {
+        const uint32_t ecur = e0 + u;
+        if (ecur < ee) {
+          while (ecur == segEnd) { flush(); advance(); }
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++)
+            if (act[ch]) {
+              const float4 v = lds128(sa + u * ROWB + ch * L * 16);
+              acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
+            }
+        }
+      }
+    }
+    issue(g + P, slotOff);
+    slotOff += GRPB;
+    if (slotOff == RINGB) slotOff = 0;
+  }
+  flush();
+  while (cur + 1 < r1) { advance(); flush(); }
+}
+
 // ----------------------------------------------------------- fix-up kernel ---
 // One worker per heavy row: out[R] = epilogue(out[R] + sum_k carry[slot0 + k]), k ascending.
 template <int VEC, int L, int NCH, int U>
@@ -414,8 +758,37 @@ sg_fixup_kernel(const SgParams p) {
 // H=256 10.9 vs 9.9 ms; Reddit-shaped H=64 3.68 vs 3.18 ms).  ROC_SG_VARIANT=a|s forces one.
 static int sg_variant_env() {
   static int v = -2;
-  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'a' ? 0 : 1); }
+  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'a' ? 0 : (e[0] == 'c' ? 2 : 1)); }
   return v;
+}
+static int sg_deep_env() {   // ROC_SG_DEEP=1: variant C with a 2x deeper ring (experiments)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ROC_SG_DEEP"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
+template <int L, int NCH, int GROUP, int P>
+static cudaError_t launch_c(const SgParams& p, unsigned grid, cudaStream_t st) {
+  constexpr int WPB = SG_THREADS / L;
+  constexpr size_t smem = (size_t)WPB * GROUP * P * NCH * L * sizeof(float4);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sg_chunk_kernel_c2<L, NCH, GROUP, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  sg_chunk_kernel_c2<L, NCH, GROUP, P><<<grid, SG_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// variant C rings: DEPTH = GROUP * P row slots per worker, 64 KB per CTA (128 KB with ROC_SG_DEEP=1)
+template <int L, int NCH>
+static cudaError_t launch_c_cfg(const SgParams& p, unsigned grid, cudaStream_t st) {
+  const bool deep = sg_deep_env() == 1;
+  if constexpr (NCH == 1) return deep ? launch_c<L, NCH, 4, 8>(p, grid, st) : launch_c<L, NCH, 4, 4>(p, grid, st);
+  else if constexpr (NCH == 2) return deep ? launch_c<L, NCH, 2, 8>(p, grid, st) : launch_c<L, NCH, 2, 4>(p, grid, st);
+  else if constexpr (NCH == 4) return deep ? launch_c<L, NCH, 1, 8>(p, grid, st) : launch_c<L, NCH, 1, 4>(p, grid, st);
+  else return deep ? launch_c<L, NCH, 1, 4>(p, grid, st) : launch_c<L, NCH, 1, 2>(p, grid, st);
 }
 
 template <int VEC, int L, int NCH, int U, int MINB>
@@ -424,10 +797,24 @@ static int launch_cfg(const SgParams& p, cudaStream_t st) {
   if (p.numChunks) {
     unsigned grid = (p.numChunks + WPB - 1) / WPB;
     int variant = sg_variant_env();
-    if (variant < 0) variant = (L == 32 || p.dense) ? 1 : 0;
-    if (variant == 0) sg_chunk_kernel<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
-    else sg_chunk_kernel_s<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
-    ROC_LAUNCH_CHECK();
+    // default: rows wider than 128 floats (NCH >= 2) stage through shared memory (variant C),
+    // everything else uses the register variant A (R-MAT-22, r1 run 13, A vs C in ms:
+    // H=16 1.33/1.58, H=41 2.41/3.09, H=64 2.39/2.95, H=128 4.03/4.59, H=256 8.25/7.47)
+    if (variant < 0) variant = (NCH >= 2 && VEC == 4) ? 2 : 0;
+    bool done = false;
+    if constexpr (VEC == 4) {
+      if (variant == 2) {
+        cudaError_t e = launch_c_cfg<L, NCH>(p, grid, st);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        done = true;
+      }
+    }
+    if (!done) {
+      if (variant == 0) sg_chunk_kernel<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
+      else sg_chunk_kernel_s<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
+      ROC_LAUNCH_CHECK();
+    }
   }
   if (p.numHeavy) {
     unsigned grid = (p.numHeavy + WPB - 1) / WPB;

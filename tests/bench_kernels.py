@@ -47,6 +47,9 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--graph", default="rmat", choices=["rmat", "reddit", "products"])
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--epi", type=int, default=0, help="ROC_SG_EPI_* flags for our kernel")
+    ap.add_argument("--zero-rows", type=float, default=0.0, help="fraction of input rows set to zero")
+    ap.add_argument("--scale-in", type=float, default=1.0, help="multiply the input (e.g. 1e-30 for tiny values)")
     a = ap.parse_args()
     dev = "cuda"
     if a.graph == "rmat":
@@ -66,10 +69,12 @@ def main():
         rp, es = ref.edge_structs(col, re, 0, 0)
     for h in [int(v) for v in a.hs.split(",")]:
         x = K.padded(n, h, dev)
-        x.copy_(torch.rand((n, h), device=dev) - 0.5)
+        x.copy_((torch.rand((n, h), device=dev) - 0.5) * a.scale_in)
+        if a.zero_rows > 0:
+            x[torch.rand(n, device=dev) < a.zero_rows] = 0
         out = K.padded(n, h, dev)
         plan.reserve(h)
-        ms = timeit(lambda: plan.forward(x, out=out), a.iters, flush)
+        ms = timeit(lambda: plan.forward(x, out=out, epilogue=a.epi), a.iters, flush)
         rec = {"H": h, "ours_ms": ms, "ours_GBps": sg_bytes(n, e, h) / ms / 1e6, "ours_Gedges_s": e / ms / 1e6}
         if use_ref and h <= 512:
             xd = x.contiguous()

@@ -172,6 +172,20 @@ def test_indegree_norm_bit_exact(h):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+def test_row_uniform_division_is_ieee():
+    """The fused norm epilogues use a shared-reciprocal + FMA division; it must equal `x / sqrtf(deg)`
+    for EVERY fp32 bit pattern x (all 2^32, incl. zeros, denormals, inf, nan) — checked for a spread of
+    degrees (incl. ones whose sqrt has an all-ones mantissa neighbourhood) and a few raw divisors."""
+    degs = [1, 2, 3, 5, 7, 16, 17, 63, 64, 65, 492, 1000, 4095, 4096, 97569, 16777215, 2 ** 31 - 1]
+    divisors = [float(np.sqrt(np.float32(d))) for d in degs] + [0.0, 1e-30, 3e38, float("inf")]
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for d in divisors:
+        rc = _lib.lib.roc_selftest_rowdiv(d, 0, 1 << 32, bad.data_ptr(), None)
+        assert rc == 0
+    torch.cuda.synchronize()
+    assert int(bad[0]) == 0, "%d of %d quotients differ from div.rn" % (int(bad[0]), len(divisors) << 32)
+
+
 def test_activation_add():
     r = np.random.RandomState(3)
     x, dy = r.randn(333, 41).astype(np.float32), r.randn(333, 41).astype(np.float32)
