@@ -143,6 +143,27 @@ int roc_sg_backward(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft, in
                     const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
                     const float* outGrad, float* inGrad, roc_stream_t stream);
 
+/* ----------------------------------------------------------------- halo --- */
+
+/* Boundary-node structures of one partition (multi-GPU).  The reference hands every
+ * partition the WHOLE input region before ScatterGather (scattergather.cc:69-73); here a
+ * partition receives only the distinct remote rows its edges read.  From the partition's
+ * sources (global ids, device) builds
+ *   ids[nHalo]      sorted distinct sources outside [rowLeft, rowRight] (grouped by owner,
+ *                   since partitions are contiguous id ranges)
+ *   colLocal[nEdges] = src - rowLeft (own rows) | Nloc + rank in ids (halo rows)
+ * — a private, derived copy; colSrc stays the canonical CSR.  Synchronises the stream. */
+typedef struct roc_halo roc_halo;
+int roc_halo_create(roc_vid_t rowLeft, roc_vid_t rowRight, uint64_t nEdges, const roc_vid_t* colSrc,
+                    roc_stream_t stream, roc_halo** out);
+void roc_halo_destroy(roc_halo* h);
+uint32_t roc_halo_size(const roc_halo* h);
+const roc_vid_t* roc_halo_ids(const roc_halo* h);         /* device */
+const roc_vid_t* roc_halo_col_local(const roc_halo* h);   /* device */
+/* dst[j][0:H] = src[rows[j]][0:H]: packs the rows another partition asked for into a send buffer. */
+int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const float* src, int64_t ldSrc,
+                  float* dst, int64_t ldDst, roc_stream_t stream);
+
 /* ---------------------------------------------------------- elementwise --- */
 
 /* Replaces norm_coop_kernel, graphnorm_kernel.cu:19-57 (fwd and bwd :126-136):

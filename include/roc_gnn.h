@@ -101,6 +101,13 @@ struct Graph {  /* gnn.h:120-130; ctor = gnn.cc:751-872 (reads <file>.add_self_e
   E_ID* d_rowEnd;
   V_ID* d_colSrc;
   roc_sg_plan* plan;
+  /* numParts > 1: halo exchange structures (derived and private; see roc_halo_* in roc_b200.h).
+   * The plan is then built on the remapped col ([own rows | halo rows]); d_colSrc stays canonical. */
+  roc_halo* halo;
+  V_ID numHalo;
+  std::vector<size_t> recvCounts, recvOffs, sendCounts, sendOffs;   /* rows, per peer partition */
+  V_ID* d_sendRows;      /* local rows other partitions read, grouped by requester */
+  size_t numSendRows;
 private:
   void build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc);
 };

@@ -59,6 +59,12 @@ PROTOTYPES = {
     "roc_sg_forward_planned": (i32, [vp, i32, vp, i64, vp, i64, i32, vp]),
     "roc_sg_forward": (i32, [u32, u32, u64, i32, vp, vp, vp, vp, vp]),
     "roc_sg_backward": (i32, [u32, u32, u64, i32, vp, vp, vp, vp, vp]),
+    "roc_halo_create": (i32, [u32, u32, u64, vp, vp, C.POINTER(vp)]),
+    "roc_halo_destroy": (None, [vp]),
+    "roc_halo_size": (u32, [vp]),
+    "roc_halo_ids": (vp, [vp]),
+    "roc_halo_col_local": (vp, [vp]),
+    "roc_pack_rows": (i32, [i64, i32, vp, vp, i64, vp, i64, vp]),
     "roc_indegree_norm": (i32, [u32, u32, u64, i32, vp, vp, i64, vp, i64, vp, vp]),
     "roc_activation_fwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp]),
     "roc_activation_bwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp, i64, i32, vp]),

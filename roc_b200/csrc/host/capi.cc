@@ -40,6 +40,7 @@ void roc_host_destroy(roc_host* h) {
   if (!h) return;
   if (h->rt) h->rt->synchronize();
   if (h->graph && h->graph->plan) roc_sg_plan_destroy(h->graph->plan);
+  if (h->graph && h->graph->halo) roc_halo_destroy(h->graph->halo);
   if (h->model) { for (GnnOp* op : h->model->layers) delete op; }
   delete h->adam;
   delete h->model;

@@ -2,6 +2,8 @@
 // edge-balanced vertex-range partition, this process's CSR slice in HBM.
 // Mirrors Graph::Graph (gnn.cc:751-872), load_graph_impl (load_task.cu:201-245)
 // and init_task_impl's CSR build (load_task.cu:296-330) without Legion regions.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "host_internal.h"
@@ -48,7 +50,67 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   d_colSrc = d_rawCols;
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   plan = nullptr;
-  ROC_CHECK(roc_sg_plan_create(rowLeft, rowRight, colLeft, d_rowEnd, d_colSrc, rt->stream, &plan));
+  halo = nullptr; numHalo = 0; d_sendRows = nullptr; numSendRows = 0;
+  const char* he = getenv("ROC_B200_HALO");
+  const bool useHalo = rt->numParts > 1 && rt->commReady && !(he && he[0] == '0');
+  if (!useHalo) {
+    ROC_CHECK(roc_sg_plan_create(rowLeft, rowRight, colLeft, d_rowEnd, d_colSrc, rt->stream, &plan));
+    return;
+  }
+  // ---- halo: which remote rows do my edges read, and which of my rows do the others read
+  const int P = rt->numParts, me = rt->myPart;
+  ROC_CHECK(roc_halo_create(rowLeft, rowRight, (uint64_t)eloc, d_colSrc, rt->stream, &halo));
+  numHalo = roc_halo_size(halo);
+  std::vector<V_ID> hid(numHalo ? numHalo : 1);
+  if (numHalo)
+    ROC_CHECK(cudaMemcpyAsync(hid.data(), roc_halo_ids(halo), (size_t)numHalo * sizeof(V_ID), cudaMemcpyDeviceToHost, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  recvCounts.assign((size_t)P, 0); recvOffs.assign((size_t)P, 0);
+  sendCounts.assign((size_t)P, 0); sendOffs.assign((size_t)P, 0);
+  {
+    size_t k = 0;   // the halo is sorted by global id == grouped by owner (contiguous ranges)
+    for (int q = 0; q < P; q++) {
+      recvOffs[(size_t)q] = k;
+      while (k < numHalo && hid[k] <= vbounds[2 * q + 1]) k++;
+      recvCounts[(size_t)q] = k - recvOffs[(size_t)q];
+    }
+    ROC_ASSERT(k == numHalo && recvCounts[(size_t)me] == 0);
+  }
+  // everyone learns everyone's request counts (P x P matrix), then the id lists travel to their owners
+  int* d_cnt = (int*)rt->dmalloc(sizeof(int) * (size_t)P * (size_t)(P + 1));
+  std::vector<int> mine((size_t)P), all((size_t)P * P);
+  for (int q = 0; q < P; q++) mine[(size_t)q] = (int)recvCounts[(size_t)q];
+  ROC_CHECK(cudaMemcpyAsync(d_cnt, mine.data(), sizeof(int) * P, cudaMemcpyHostToDevice, rt->stream));
+  ROC_CHECK(rt->comm.allgather_i32(d_cnt, d_cnt + P, (size_t)P, rt->stream));
+  ROC_CHECK(cudaMemcpyAsync(all.data(), d_cnt + P, sizeof(int) * (size_t)P * P, cudaMemcpyDeviceToHost, rt->stream));
+  ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  numSendRows = 0;
+  for (int q = 0; q < P; q++) {
+    sendOffs[(size_t)q] = numSendRows;
+    sendCounts[(size_t)q] = (size_t)all[(size_t)q * P + me];   // rows of mine that partition q reads
+    numSendRows += sendCounts[(size_t)q];
+  }
+  d_sendRows = (V_ID*)rt->dmalloc(sizeof(V_ID) * (numSendRows ? numSendRows : 1));
+  ROC_CHECK(rt->comm.alltoallv(roc_halo_ids(halo), recvCounts, recvOffs, d_sendRows, sendCounts, sendOffs,
+                               /*isFloat=*/false, rt->stream));
+  {
+    std::vector<V_ID> rows(numSendRows ? numSendRows : 1);
+    if (numSendRows)
+      ROC_CHECK(cudaMemcpyAsync(rows.data(), d_sendRows, numSendRows * sizeof(V_ID), cudaMemcpyDeviceToHost, rt->stream));
+    ROC_CHECK(cudaStreamSynchronize(rt->stream));
+    for (size_t j = 0; j < numSendRows; j++) {
+      ROC_ASSERT(rows[j] >= rowLeft && rows[j] <= rowRight);
+      rows[j] -= rowLeft;                                       // global id -> my local row
+    }
+    if (numSendRows)
+      ROC_CHECK(cudaMemcpyAsync(d_sendRows, rows.data(), numSendRows * sizeof(V_ID), cudaMemcpyHostToDevice, rt->stream));
+    ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  }
+  fprintf(stderr, "[roc_b200] part %d/%d: halo %u rows (%.1f%% of the %u remote vertices), sends %zu rows\n", me, P,
+          numHalo, 100.0 * numHalo / std::max<double>(1.0, (double)numNodes - (double)nloc), (unsigned)(numNodes - nloc),
+          numSendRows);
+  // the kernel indexes [own rows | halo rows]; rowEnd offsets are unchanged
+  ROC_CHECK(roc_sg_plan_create(rowLeft, rowRight, colLeft, d_rowEnd, roc_halo_col_local(halo), rt->stream, &plan));
 }
 
 Graph::Graph(Context ctx, Runtime* /*runtime*/, const Config& config)

@@ -35,6 +35,8 @@ struct TensorImpl {
   bool isWeight = false;
   bool requiresGrad = false;
   bool produced = false;  // output of some op
+  int64_t haloData = 0;   // extra rows after the local ones: halo slab of a ScatterGather input
+  int64_t haloGrad = 0;   // same for the gradient twin (backward ScatterGather reads it)
   float* data = nullptr;  // lazily allocated (node tensors)
   float* grad = nullptr;
   int32_t* labelIdx = nullptr;   // compact labels when loaded through load_labels / set_labels
@@ -54,6 +56,11 @@ struct Comm {
                  const std::vector<size_t>& offsets, cudaStream_t st);
   int allreduce_sum(float* buf, size_t count, cudaStream_t st);
   int allreduce_sum_i32(int* buf, size_t count, cudaStream_t st);
+  int allgather_i32(const int* sendbuf, int* recvbuf, size_t countPerRank, cudaStream_t st);
+  // all-to-all-v by grouped ncclSend / ncclRecv (counts and offsets in elements; no self transfer)
+  int alltoallv(const void* sendbuf, const std::vector<size_t>& sendCounts, const std::vector<size_t>& sendOffs,
+                void* recvbuf, const std::vector<size_t>& recvCounts, const std::vector<size_t>& recvOffs,
+                bool isFloat, cudaStream_t st);
   void destroy();
 };
 
@@ -65,7 +72,9 @@ struct RuntimeImpl {
   Comm comm;
   bool commReady = false;
   // shared scratch
-  float* gatherBuf = nullptr; size_t gatherFloats = 0;   // [numNodes][maxLd] when numParts > 1
+  float* gatherBuf = nullptr; size_t gatherFloats = 0;   // [numNodes][maxLd]: all-gather fallback (ROC_B200_HALO=0)
+  float* sendBuf = nullptr; size_t sendFloats = 0;       // packed rows other partitions asked for
+  void ensure_sendbuf(size_t floats);
   void* linWs = nullptr; size_t linWsBytes = 0;           // split-K workspace of Linear backward
   void* staging = nullptr; size_t stagingBytes = 0;       // H2D staging for dense host rows -> padded rows
   float* flatGrad = nullptr; size_t flatGradCount = 0;    // all dW, one all-reduce

@@ -194,7 +194,19 @@ bool Model::init(const Config& config) {
   rt->ensure_lin_ws(ws);
   if (maxSg > 0) {
     ROC_CHECK(roc_sg_plan_reserve(myGraph.plan, maxSg));
-    if (rt->numParts > 1) rt->ensure_gather((size_t)myGraph.numNodes * (size_t)round_up4(maxSg));
+    if (rt->numParts > 1 && !myGraph.halo) rt->ensure_gather((size_t)myGraph.numNodes * (size_t)round_up4(maxSg));
+    if (myGraph.halo) {
+      // the tensors a ScatterGather reads get the halo slab appended to their own rows
+      rt->ensure_sendbuf((myGraph.numSendRows ? myGraph.numSendRows : 1) * (size_t)round_up4(maxSg));
+      for (size_t l = 0; l < layers.size(); l++) {
+        if (!as<ScatterGather>(layers[l])) continue;
+        TensorImpl& xin = rt->t(layers[l]->inputs[0].region);
+        TensorImpl& xout = rt->t(layers[l]->outputs[0].region);
+        ROC_ASSERT(xin.data == nullptr && xout.grad == nullptr);   // lazily allocated: not touched yet
+        xin.haloData = myGraph.numHalo;
+        xout.haloGrad = myGraph.numHalo;
+      }
+    }
   }
   // ---- fusion of  linear -> indegree_norm -> scatter_gather -> indegree_norm -> relu  (gnn.cc:81-85)
   if (fuse) {
@@ -432,11 +444,25 @@ namespace {
 // The exchange step of ScatterGather (scattergather.cc:69-73 asks Legion for the
 // WHOLE input region): all-gather every partition's slab into [numNodes][ld] so
 // the kernel can index rows by global source id.  numParts == 1: no copy at all.
-const float* gathered(const Model& model, const float* local, int64_t ld) {
+// Default for numParts > 1: the halo exchange — each partition packs the rows the others read
+// (roc_pack_rows), one grouped NCCL send/recv moves them, and they land right behind the
+// partition's own rows ([Nloc | halo] is what the remapped col indexes).  ROC_B200_HALO=0 keeps
+// the whole-matrix all-gather (the reference's semantics) for comparison.
+const float* gathered(const Model& model, float* local, int64_t ld, int H) {
   RuntimeImpl* rt = model.ctx;
   if (rt->numParts == 1) return local;
   ROC_ASSERT(rt->commReady);
   const Graph& g = model.myGraph;
+  if (g.halo) {
+    const size_t uld = (size_t)ld;
+    rt->ensure_sendbuf((g.numSendRows ? g.numSendRows : 1) * uld);
+    ROC_CHECK(roc_pack_rows((int64_t)g.numSendRows, H, g.d_sendRows, local, ld, rt->sendBuf, ld, rt->stream));
+    std::vector<size_t> sc(g.sendCounts), so(g.sendOffs), rc(g.recvCounts), ro(g.recvOffs);
+    for (size_t q = 0; q < sc.size(); q++) { sc[q] *= uld; so[q] *= uld; rc[q] *= uld; ro[q] *= uld; }
+    float* haloBase = local + (size_t)model.local_rows() * uld;
+    ROC_CHECK(rt->comm.alltoallv(rt->sendBuf, sc, so, haloBase, rc, ro, /*isFloat=*/true, rt->stream));
+    return local;
+  }
   rt->ensure_gather((size_t)g.numNodes * (size_t)ld);
   std::vector<size_t> counts((size_t)rt->numParts), offs((size_t)rt->numParts);
   for (int r = 0; r < rt->numParts; r++) {
@@ -453,7 +479,7 @@ void ScatterGather::forward(const Model& model) {
   const int H = (int)inputs[0].dims[0];
   const int64_t ldIn = rt->t(inputs[0].region).ld;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
-  const float* src = gathered(model, rt->data(inputs[0].region), ldIn);
+  const float* src = gathered(model, rt->data(inputs[0].region), ldIn, H);
   float* dst = rt->data(outRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, dst, rt->t(outRegion).ld, epilogue, rt->stream));
@@ -468,7 +494,7 @@ void ScatterGather::backward(const Model& model) {
   const int64_t ld = rt->t(outputs[0].region).ld;
   const int dstRegion = bwdOut >= 0 ? bwdOut : inputs[0].region;
   // Forward and backward do exactly the same thing, on gradients (scattergather_kernel.cu:168-169)
-  const float* src = gathered(model, rt->grad(outputs[0].region), ld);
+  const float* src = gathered(model, rt->grad(outputs[0].region), ld, H);
   float* dst = rt->grad(dstRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, dst, rt->t(dstRegion).ld, bwdEpilogue, rt->stream));

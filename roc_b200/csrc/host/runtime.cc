@@ -45,7 +45,7 @@ int RuntimeImpl::new_tensor(int64_t rows, int H, int64_t ld, bool isInt, bool is
 float* RuntimeImpl::data(int region) {
   TensorImpl& x = t(region);
   if (!x.data) {
-    size_t bytes = (size_t)x.rows * (size_t)x.ld * sizeof(float);
+    size_t bytes = (size_t)(x.rows + x.haloData) * (size_t)x.ld * sizeof(float);
     x.data = (float*)dmalloc(bytes);
     ROC_CHECK(cudaMemsetAsync(x.data, 0, bytes ? bytes : 16, stream));
   }
@@ -55,7 +55,7 @@ float* RuntimeImpl::data(int region) {
 float* RuntimeImpl::grad(int region) {
   TensorImpl& x = t(region);
   if (!x.grad) {
-    size_t bytes = (size_t)x.rows * (size_t)x.ld * sizeof(float);
+    size_t bytes = (size_t)(x.rows + x.haloGrad) * (size_t)x.ld * sizeof(float);
     x.grad = (float*)dmalloc(bytes);
     ROC_CHECK(cudaMemsetAsync(x.grad, 0, bytes ? bytes : 16, stream));
   }
@@ -80,6 +80,12 @@ void RuntimeImpl::sg_end() {
   ROC_CHECK(cudaEventRecord(sgTimings.back().b, stream));
 }
 
+void RuntimeImpl::ensure_sendbuf(size_t floats) {
+  if (floats <= sendFloats) return;
+  sendBuf = (float*)dmalloc(floats * sizeof(float));
+  sendFloats = floats;
+}
+
 void RuntimeImpl::ensure_staging(size_t bytes) {
   if (bytes <= stagingBytes) return;
   staging = dmalloc(bytes);
@@ -102,6 +108,9 @@ struct NcclFns {
   ncclResult_t (*GroupEnd)();
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
 };
 NcclFns g_nccl;
@@ -128,6 +137,9 @@ bool load_nccl() {
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(Broadcast, "ncclBroadcast");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   g_ncclLib = h;
@@ -181,6 +193,28 @@ int Comm::allreduce_sum(float* buf, size_t count, cudaStream_t st) {
 
 int Comm::allreduce_sum_i32(int* buf, size_t count, cudaStream_t st) {
   return g_nccl.AllReduce(buf, buf, count, ncclInt32, ncclSum, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
+}
+
+int Comm::allgather_i32(const int* sendbuf, int* recvbuf, size_t countPerRank, cudaStream_t st) {
+  return g_nccl.AllGather(sendbuf, recvbuf, countPerRank, ncclInt32, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
+}
+
+int Comm::alltoallv(const void* sendbuf, const std::vector<size_t>& sendCounts, const std::vector<size_t>& sendOffs,
+                    void* recvbuf, const std::vector<size_t>& recvCounts, const std::vector<size_t>& recvOffs,
+                    bool isFloat, cudaStream_t st) {
+  // one grouped ncclSend + ncclRecv per peer: NVSwitch gives every pair full bandwidth, so the
+  // group is a single fused transfer; 4-byte elements either way
+  ncclComm_t c = (ncclComm_t)comm;
+  const ncclDataType_t dt = isFloat ? ncclFloat : ncclUint32;
+  const char* sb = static_cast<const char*>(sendbuf);
+  char* rb = static_cast<char*>(recvbuf);
+  if (g_nccl.GroupStart() != ncclSuccess) return -1;
+  for (int q = 0; q < world; q++) {
+    if (q == rank) continue;
+    if (sendCounts[q] && g_nccl.Send(sb + sendOffs[q] * 4, sendCounts[q], dt, q, c, st) != ncclSuccess) { g_nccl.GroupEnd(); return -2; }
+    if (recvCounts[q] && g_nccl.Recv(rb + recvOffs[q] * 4, recvCounts[q], dt, q, c, st) != ncclSuccess) { g_nccl.GroupEnd(); return -3; }
+  }
+  return g_nccl.GroupEnd() == ncclSuccess ? 0 : -4;
 }
 
 void Comm::destroy() {

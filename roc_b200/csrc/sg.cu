@@ -39,11 +39,12 @@ constexpr int SG_THREADS = 256;    // threads per CTA
 }  // namespace roc
 
 struct roc_sg_plan {
-  uint32_t nloc = 0, E = 0, numChunks = 0, numCarries = 0, numHeavy = 0;
+  uint32_t nloc = 0, E = 0, numChunks = 0, numCarries = 0, numHeavy = 0, numBig = 0;
   uint32_t* rs = nullptr;         // [nloc+1]   local row starts (rs[r+1] = rowEnd[r]-colLeft)
   uint32_t* firstRow = nullptr;   // [numChunks+1] first row whose start >= c*CH
   uint32_t* carryIdx = nullptr;   // [numChunks+1] exclusive scan of carry-in flags
-  uint32_t* heavyRows = nullptr;  // [numHeavy]  rows with degree > CH
+  uint32_t* heavyRows = nullptr;  // [numHeavy]  rows with degree > CH and <= 32 carries (one worker each)
+  uint32_t* bigRows = nullptr;    // [numBig]    rows with more carries (one CTA each)
   const uint32_t* col = nullptr;  // caller's colSrc
   float* carry = nullptr;         // [numCarries][carryLd]
   size_t carryLd = 0;
@@ -90,9 +91,15 @@ __global__ void k_carry_flag(uint32_t numChunks, const uint32_t* __restrict__ rs
   flag[c] = f;
 }
 
-__global__ void k_heavy_flag(uint32_t nloc, const uint32_t* __restrict__ rs, uint8_t* __restrict__ flag) {
+__global__ void k_heavy_flag(uint32_t nloc, const uint32_t* __restrict__ rs, uint8_t* __restrict__ flag,
+                             uint8_t* __restrict__ bigFlag) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < nloc) flag[r] = (rs[r + 1] - rs[r] > (uint32_t)SG_CH) ? 1 : 0;
+  if (r >= nloc) return;
+  const uint32_t s = rs[r], t = rs[r + 1];
+  const bool heavy = t - s > (uint32_t)SG_CH;
+  const uint32_t carries = heavy ? (t - 1) / SG_CH - s / SG_CH : 0;
+  flag[r] = (heavy && carries <= 32u) ? 1 : 0;      // 32 == SG_BIG
+  bigFlag[r] = (carries > 32u) ? 1 : 0;
 }
 
 // ----------------------------------------------------------- vector helper ---
@@ -137,13 +144,14 @@ struct SgParams {
   const uint32_t* firstRow;
   const uint32_t* carryIdx;
   const uint32_t* heavyRows;
+  const uint32_t* bigRows;
   const uint32_t* col;
   const void* in;      // [*][ldIn]  (in units of T)
   void* out;           // [nloc][ldOut]
   void* carry;         // [numCarries][ldC]
   size_t ldIn, ldOut, ldC;   // in units of T (float4 or float)
   uint32_t Q;          // valid T-columns per row
-  uint32_t E, numChunks, numHeavy;
+  uint32_t E, numChunks, numHeavy, numBig;
   int epi;
   int dense;           // mean degree >= chunk size: nearly every row is cut at chunk boundaries
 };
@@ -752,6 +760,63 @@ sg_fixup_kernel(const SgParams p) {
     if (act[ch]) epi_store<VEC>(acc[ch], dst + lane + ch * L, t - s, p.epi);
 }
 
+// Rows with more than SG_BIG carries (hubs: R-MAT-22's largest row spans 1 524 chunks) get a
+// whole CTA: each of the 256/L lane groups sums a contiguous block of the carries, the blocks
+// are combined in order through shared memory.  With one worker per row the hubs' serial
+// chains set the kernel's duration (0.56 ms for 250 MB of traffic, r1 run 15).
+constexpr uint32_t SG_BIG = 32;
+
+template <int VEC, int L, int NCH, int U>
+__global__ void __launch_bounds__(SG_THREADS)
+sg_fixup_big_kernel(const SgParams p) {
+  typedef typename V<VEC>::T T;
+  constexpr int WPB = SG_THREADS / L;
+  constexpr uint32_t CH = SG_CH;
+  __shared__ __align__(16) float part[WPB * NCH * L * VEC];
+  const int lane = threadIdx.x % L;
+  const int g = threadIdx.x / L;
+  const uint32_t R = p.bigRows[blockIdx.x];
+  const uint32_t s = p.rs[R], t = p.rs[R + 1];
+  const uint32_t c0 = s / CH, cLast = (t - 1) / CH;
+  const uint32_t n = cLast - c0;
+  const uint32_t slot0 = p.carryIdx[c0 + 1];
+  const T* cbase = reinterpret_cast<const T*>(p.carry) + (size_t)slot0 * p.ldC;
+  const uint32_t per = (n + WPB - 1) / WPB;
+  const uint32_t k0 = min(n, (uint32_t)g * per), k1 = min(n, k0 + per);
+  bool act[NCH];
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) { act[ch] = (uint32_t)(lane + ch * L) < p.Q; acc[ch] = V<VEC>::zero(); }
+  for (uint32_t k = k0; k < k1; k += U) {
+    T v[U][NCH];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++)
+        v[u][ch] = (k + u < k1 && act[ch]) ? V<VEC>::ld_plain(cbase + (size_t)(k + u) * p.ldC + lane + ch * L)
+                                           : V<VEC>::zero();
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+  }
+  T* sp = reinterpret_cast<T*>(part);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) sp[(g * NCH + ch) * L + lane] = acc[ch];
+  __syncthreads();
+  if (g == 0) {
+    T* dst = reinterpret_cast<T*>(p.out) + (size_t)R * p.ldOut;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      if (act[ch]) {
+        T a = V<VEC>::ld_plain(dst + lane + ch * L);      // the owner chunk's raw partial
+        for (int gg = 0; gg < WPB; gg++) V<VEC>::add(a, sp[(gg * NCH + ch) * L + lane]);
+        epi_store<VEC>(a, dst + lane + ch * L, t - s, p.epi);
+      }
+    }
+  }
+}
+
 // Loop shape: A (per-edge row test, gathers overlap across short rows) wins on
 // sparse graphs with narrow rows, S (one store site) on wide rows and on dense
 // graphs where almost every row spans chunks (r1 run 3: R-MAT-22 H=16 1.42 vs 2.05 ms,
@@ -821,6 +886,10 @@ static int launch_cfg(const SgParams& p, cudaStream_t st) {
     sg_fixup_kernel<VEC, L, NCH, U><<<grid, SG_THREADS, 0, st>>>(p);
     ROC_LAUNCH_CHECK();
   }
+  if (p.numBig) {
+    sg_fixup_big_kernel<VEC, L, NCH, U><<<p.numBig, SG_THREADS, 0, st>>>(p);
+    ROC_LAUNCH_CHECK();
+  }
   return ROC_OK;
 }
 
@@ -873,7 +942,7 @@ extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid
   cudaGetDevice(&pl->device);
   pl->nloc = nloc; pl->E = (uint32_t)E64; pl->col = colSrc;
   pl->numChunks = pl->E / SG_CH + 1;
-  uint32_t* flag = nullptr; uint8_t* hflag = nullptr; void* tmp = nullptr; uint32_t* dcount = nullptr;
+  uint32_t* flag = nullptr; uint8_t* hflag = nullptr; uint8_t* bflag = nullptr; void* tmp = nullptr; uint32_t* dcount = nullptr;
   int rc = ROC_OK;
   auto fail = [&](int code) { rc = code; };
 #define PL_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail((int)e_); goto done; } } while (0)
@@ -892,7 +961,9 @@ extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid
     count_launch();
     k_carry_flag<<<(pl->numChunks + 1 + T - 1) / T, T, 0, st>>>(pl->numChunks, pl->rs, pl->firstRow, flag);
     count_launch();
-    k_heavy_flag<<<(nloc + T - 1) / T, T, 0, st>>>(nloc, pl->rs, hflag);
+    PL_CUDA(cudaMalloc(&bflag, (size_t)nloc));
+    PL_CUDA(cudaMalloc(&pl->bigRows, sizeof(uint32_t) * (size_t)nloc));
+    k_heavy_flag<<<(nloc + T - 1) / T, T, 0, st>>>(nloc, pl->rs, hflag, bflag);
     count_launch();
     PL_CUDA(cudaGetLastError());
     size_t tb1 = 0, tb2 = 0;
@@ -903,14 +974,16 @@ extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid
     PL_CUDA(cudaMalloc(&tmp, tb ? tb : 16));
     PL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, flag, pl->carryIdx, (int)(pl->numChunks + 1), st));
     PL_CUDA(cub::DeviceSelect::Flagged(tmp, tb2, cnt, hflag, pl->heavyRows, dcount, (int)nloc, st));
-    count_launch(4);
-    PL_CUDA(cudaMemcpyAsync(&pl->numCarries, pl->carryIdx + pl->numChunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(&pl->numHeavy, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cub::DeviceSelect::Flagged(tmp, tb2, cnt, bflag, pl->bigRows, dcount, (int)nloc, st));
+    count_launch(6);
+    PL_CUDA(cudaMemcpyAsync(&pl->numCarries, pl->carryIdx + pl->numChunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMemcpyAsync(&pl->numBig, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaStreamSynchronize(st));
   }
 done:
 #undef PL_CUDA
-  cudaFree(flag); cudaFree(hflag); cudaFree(tmp); cudaFree(dcount);
+  cudaFree(flag); cudaFree(hflag); cudaFree(bflag); cudaFree(tmp); cudaFree(dcount);
   if (rc != ROC_OK) { roc_sg_plan_destroy(pl); return rc; }
   *planOut = pl;
   return ROC_OK;
@@ -918,7 +991,7 @@ done:
 
 extern "C" void roc_sg_plan_destroy(roc_sg_plan* pl) {
   if (!pl) return;
-  cudaFree(pl->rs); cudaFree(pl->firstRow); cudaFree(pl->carryIdx); cudaFree(pl->heavyRows); cudaFree(pl->carry);
+  cudaFree(pl->rs); cudaFree(pl->firstRow); cudaFree(pl->carryIdx); cudaFree(pl->heavyRows); cudaFree(pl->bigRows); cudaFree(pl->carry);
   delete pl;
 }
 
@@ -932,7 +1005,7 @@ extern "C" int roc_sg_plan_info(const roc_sg_plan* pl, uint64_t* numChunks, uint
   if (!pl) return ROC_ERR_INVALID;
   if (numChunks) *numChunks = pl->numChunks;
   if (numCarries) *numCarries = pl->numCarries;
-  if (numHeavyRows) *numHeavyRows = pl->numHeavy;
+  if (numHeavyRows) *numHeavyRows = (uint64_t)pl->numHeavy + pl->numBig;
   return ROC_OK;
 }
 
@@ -952,9 +1025,9 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
   for (int c0 = 0; c0 < H; c0 += blockCols) {
     int hb = (H - c0 < blockCols) ? H - c0 : blockCols;
     SgParams p;
-    p.rs = pl->rs; p.firstRow = pl->firstRow; p.carryIdx = pl->carryIdx; p.heavyRows = pl->heavyRows;
+    p.rs = pl->rs; p.firstRow = pl->firstRow; p.carryIdx = pl->carryIdx; p.heavyRows = pl->heavyRows; p.bigRows = pl->bigRows;
     p.col = pl->col; p.in = in + c0; p.out = out + c0; p.carry = pl->carry;
-    p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.epi = epilogue;
+    p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.numBig = pl->numBig; p.epi = epilogue;
     p.dense = (pl->nloc > 0 && pl->E / pl->nloc >= (uint32_t)SG_CH) ? 1 : 0;
     int rc;
     if (vec) {

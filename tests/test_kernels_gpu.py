@@ -138,6 +138,57 @@ def test_sg_round_trip_properties_large():
     assert torch.allclose(ax, want, rtol=1e-4, atol=1e-4)
 
 
+class _DevArr:
+    """int32 view of library-owned device memory through __cuda_array_interface__."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def _dev_view(ptr, n):
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int32, device=DEV)
+    return torch.as_tensor(_DevArr(ptr, n), device=DEV).clone()
+
+
+def test_halo_structures_bit_exact():
+    """roc_halo_*: sorted distinct remote sources, remapped col, row packing — against numpy."""
+    row_end, col = graph("rmat")
+    n = row_end.shape[0]
+    k, vb, eb = oracle.partition(row_end, 4)
+    x = np.random.RandomState(3).randn(n, 12).astype(np.float32)
+    for c in range(4):
+        rl, rr, cl, cr = int(vb[c, 0]), int(vb[c, 1]), int(eb[c, 0]), int(eb[c, 1])
+        cs = col[cl:cr + 1]
+        d_col = torch.from_numpy(cs.astype(np.int32)).to(DEV)
+        h = C.c_void_p()
+        assert _lib.lib.roc_halo_create(rl, rr, cs.shape[0], d_col.data_ptr(), None, C.byref(h)) == 0
+        nh = _lib.lib.roc_halo_size(h)
+        remote = np.unique(cs[(cs < rl) | (cs > rr)])
+        assert nh == remote.shape[0]
+        torch.cuda.synchronize()
+        got_ids = _dev_view(_lib.lib.roc_halo_ids(h), nh)
+        got_col = _dev_view(_lib.lib.roc_halo_col_local(h), cs.shape[0])
+        assert np.array_equal(got_ids.cpu().numpy().astype(np.uint32), remote)
+        nloc = rr - rl + 1
+        want_col = np.where((cs >= rl) & (cs <= rr), cs.astype(np.int64) - rl, nloc + np.searchsorted(remote, cs))
+        assert np.array_equal(got_col.cpu().numpy().astype(np.int64), want_col)
+        # SpMM over [own rows | halo rows] with the remapped col == SpMM over the whole matrix with global ids
+        buf = np.concatenate([x[rl:rr + 1], x[remote]])
+        d_re = torch.from_numpy(row_end[rl:rr + 1].astype(np.int64)).to(DEV)
+        plan = K.SgPlan(rl, rr, cl, d_re, got_col)
+        got = plan.forward(torch.from_numpy(buf).to(DEV), out=torch.empty((nloc, 12), device=DEV))
+        want = oracle.scatter_gather(rl, rr, cl, row_end[rl:rr + 1], cs, x)
+        rel_close(got.cpu().numpy(), want, what="halo-indexed SG part %d" % c)
+        # row packing
+        rows = torch.from_numpy(np.random.RandomState(c).randint(0, nloc, size=777).astype(np.int32)).to(DEV)
+        src = K.padded(nloc, 12, DEV, fill=torch.from_numpy(x[rl:rr + 1]).to(DEV))
+        dst = K.padded(777, 12, DEV)
+        assert _lib.lib.roc_pack_rows(777, 12, rows.data_ptr(), src.data_ptr(), src.stride(0), dst.data_ptr(),
+                                      dst.stride(0), None) == 0
+        assert np.array_equal(dst.cpu().numpy(), x[rl:rr + 1][rows.cpu().numpy()])
+        _lib.lib.roc_halo_destroy(h)
+
+
 def test_build_csr_bit_exact():
     row_end, col = graph("rmat")
     k, vb, eb = oracle.partition(row_end, 3)
