@@ -25,7 +25,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
 // cross-check the tensor-core path).
 static bool force_simt() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ROC_B200_GEMM"); v = (e && e[0] == 's') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("ROC_B200_GEMM"); v = (e && e[0] == 's' && e[1] == 'i') ? 1 : 0; }
   return v == 1;
 }
 }  // namespace roc

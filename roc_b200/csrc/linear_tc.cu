@@ -18,6 +18,7 @@
 // The kernel is HBM-bound on X (rows*inDim*4 bytes read once); W (tens of KB) stays
 // in L2.  Roofline: DESIGN.md.
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -192,6 +193,202 @@ k_tc_linear_fwd(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
 }
 
+// ---------------------------------------------------------------------------
+// TS variant: the X operand reaches the tensor core through TMEM instead of smem.
+// The SS kernel above moves every X element through shared memory five times (TMA
+// write, split read, hi+lo write, 3 MMA operand reads ~ 136 KB per k-block, ~1100
+// smem cycles against ~700 cycles of HBM time for the same k-block); here the
+// split warps read the TMA tile once and tcgen05.st hi / lo straight into TMEM
+// (A operand, K-major: lane = row, column = k), so smem carries 16 KB in + 16 KB
+// out of X and the W tiles only.  12 warps:
+//   warp 0    TMA producer (X tile + W_hi + W_lo per stage)
+//   warp 1    MMA issuer: 12 x tcgen05.mma [D], [A_tmem], B_smem per stage
+//   warp 2    TMEM allocator (512 columns: 2 accumulators + `stages` A slots of 64)
+//   warps 4-7 split: smem (128B-swizzled) -> regs -> hi/lo -> tcgen05.st
+//   warps 8-11 epilogue of tile i overlaps the main loop of tile i+1 (two accumulators)
+constexpr int TS_THREADS = 512;      // launched with 384 when splitGroups == 1
+constexpr int TS_MAX_STAGES = 6;
+
+struct TcTsParams {
+  float* Y; int64_t ldY;
+  int64_t rows; int outDim; int BN; int numKb; int stages;
+  uint32_t tmemCols, dStride, aCol0;
+  int splitGroups;      // 1 or 2 warpgroups of split warps (alternate k-blocks)
+  int relu;
+  const uint64_t* rowEnd; uint64_t colLeft;
+};
+
+__device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int BN, int outDim, int64_t row, int64_t rows,
+                                                 float* Y, int64_t ldY, int relu, const uint64_t* rowEnd,
+                                                 uint64_t colLeft) {
+  float d = 1.0f;
+  if (rowEnd && row < rows) {
+    uint64_t st = (row == 0) ? colLeft : rowEnd[row - 1];
+    d = sqrtf((float)(uint32_t)(rowEnd[row] - st));
+  }
+  const RowDiv rd = rowdiv_make(d);
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (row < rows) {
+      float* y = Y + row * ldY + c0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float x = __uint_as_float(r[q * 4 + k]);
+          if (relu) x = relu_nanprop(x);
+          if (rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
+          v[k] = x;
+        }
+        const int c = c0 + q * 4;
+        if (c + 4 <= outDim) *reinterpret_cast<float4*>(y + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+#pragma unroll
+          for (int k = 0; k < 4; k++) if (c + k < outDim) y[q * 4 + k] = v[k];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
+                   const __grid_constant__ CUtensorMap mapWlo, const TcTsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t aBytes = TC_BM * TC_BK * 4;                 // 16 KB of X per stage
+  const uint32_t bBytes = (uint32_t)p.BN * TC_BK * 4;
+  const uint32_t stageBytes = aBytes + 2 * bBytes;
+  uint8_t* barBase = smem + (size_t)p.stages * stageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(barBase);    // [stages] TMA landed (X, W_hi, W_lo)
+  uint64_t* aFull = full + TS_MAX_STAGES;                   // [stages] hi/lo of X are in TMEM slot s
+  uint64_t* empty = aFull + TS_MAX_STAGES;                  // [stages] MMAs done with smem stage + TMEM slot
+  uint64_t* dFull = empty + TS_MAX_STAGES;                  // [2] accumulator complete
+  uint64_t* dEmpty = dFull + 2;                             // [2] accumulator drained by the epilogue
+  uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(dEmpty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t numTiles = (p.rows + TC_BM - 1) / TC_BM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWhi); tma_prefetch_desc(&mapWlo);
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&aFull[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&dFull[b], 1); mbar_init(&dEmpty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmemAddr, p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemAddr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.numKb; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + (size_t)s * stageBytes;
+          mbar_arrive_expect_tx(&full[s], aBytes + 2 * bBytes);
+          tma_load_2d(st, &mapX, kb * TC_BK, (int)(tile * TC_BM), &full[s]);
+          tma_load_2d(st + aBytes, &mapWhi, kb * TC_BK, 0, &full[s]);
+          tma_load_2d(st + aBytes + bBytes, &mapWlo, kb * TC_BK, 0, &full[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer =================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN, 0, 0);
+      int s = 0; uint32_t ph = 0; uint32_t tl = 0;
+      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, tl++) {
+        const uint32_t b = tl & 1u;
+        mbar_wait(&dEmpty[b], ((tl >> 1) & 1u) ^ 1u);   // the epilogue has drained accumulator b
+        tc_fence_after();
+        const uint32_t dAddr = tmemBase + b * p.dStride;
+        for (int kb = 0; kb < p.numKb; kb++) {
+          mbar_wait(&full[s], ph);                      // W tiles landed
+          mbar_wait(&aFull[s], ph);                     // X hi/lo stored to TMEM slot s
+          tc_fence_after();
+          const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)s * 64u;
+          const uint32_t aLo = aHi + 32u;
+          const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + aBytes;
+          const uint32_t bLo = bHi + bBytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; k++) {
+            const uint32_t off = k * TC_UK * 4;   // bytes along K inside the swizzled row
+            const uint64_t dBh = make_sdesc_sw128(bHi + off, 16, 1024), dBl = make_sdesc_sw128(bLo + off, 16, 1024);
+            umma_tf32_ts(dAddr, aLo + k * TC_UK, dBh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts(dAddr, aHi + k * TC_UK, dBl, idesc, 1u);
+            umma_tf32_ts(dAddr, aHi + k * TC_UK, dBh, idesc, 1u);
+          }
+          umma_commit(&empty[s]);                           // smem stage + TMEM slot reusable
+          if (kb == p.numKb - 1) umma_commit(&dFull[b]);   // accumulator of this tile complete
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + 4 * p.splitGroups) {
+    // ============== operand split: smem X tile -> hi / lo in TMEM slot s ==============
+    // group g of the split warps takes every splitGroups-th k-block, so one group's
+    // tcgen05.st / wait::st latency overlaps the other group's loads
+    const int g = (warp - 4) >> 2;
+    const int t = (threadIdx.x - 128) & 127;    // row of the tile == TMEM lane
+    const uint32_t laneBase = (uint32_t)((warp & 3) * 32) << 16;
+    const int64_t myTiles = (numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t iters = myTiles * p.numKb;
+    for (int64_t it = g; it < iters; it += p.splitGroups) {
+      const int s = (int)(it % p.stages);
+      const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+      mbar_wait(&full[s], ph);
+      // 128B swizzle: 16-byte chunk j of row t sits at chunk j ^ (t & 7)
+      const float4* xr = reinterpret_cast<const float4*>(smem + (size_t)s * stageBytes) + t * 8;
+      const uint32_t taddr = tmemBase + laneBase + p.aCol0 + (uint32_t)s * 64u;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 v = xr[(half * 4 + j) ^ (t & 7)];
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t h = __float_as_uint(e[k]) & 0xFFFFE000u;
+            hi[j * 4 + k] = h;
+            lo[j * 4 + k] = __float_as_uint(e[k] - __uint_as_float(h));
+          }
+        }
+        tmem_st16(taddr + half * 16, hi);
+        tmem_st16(taddr + 32 + half * 16, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aFull[s]);
+    }
+  } else if (warp >= 4 + 4 * p.splitGroups) {
+    // ===== epilogue: TMEM lane = row of the tile; this warp owns lanes 32*(warp%4)..+31 =====
+    uint32_t tl = 0;
+    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, tl++) {
+      const uint32_t b = tl & 1u;
+      mbar_wait(&dFull[b], (tl >> 1) & 1u);
+      tc_fence_after();
+      const int64_t row = tile * TC_BM + (warp & 3) * 32 + lane;
+      const uint32_t taddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16) + b * p.dStride;
+      tc_epilogue_rows(taddr, p.BN, p.outDim, row, p.rows, p.Y, p.ldY, p.relu, p.rowEnd, p.colLeft);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dEmpty[b]);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
+}
+
 // scratch for the split weights (grow-only, per process; the host uses one stream)
 static float* g_wsplit = nullptr;
 static size_t g_wsplitFloats = 0;
@@ -220,6 +417,35 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
   if (!make_tmap_f32_2d(&mapWhi, Whi, (uint64_t)BN, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
   if (!make_tmap_f32_2d(&mapWlo, Wlo, (uint64_t)BN, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
 
+  const int64_t numTiles = (rows + TC_BM - 1) / TC_BM;
+  int grid = sm_count();
+  if (numTiles < grid) grid = (int)numTiles;
+  {
+    // TS path: 2 accumulators of dStride columns + `stages` A slots of 64 columns in 512 TMEM columns
+    const char* g = getenv("ROC_B200_GEMM");
+    const uint32_t dStride = (uint32_t)((BN + 31) / 32 * 32);
+    const size_t stageBytesTs = (size_t)TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
+    int stagesTs = (int)((512 - 2 * dStride) / 64);
+    if (stagesTs > TS_MAX_STAGES) stagesTs = TS_MAX_STAGES;
+    while (stagesTs > 0 && (size_t)stagesTs * stageBytesTs + 1024 + 256 > (size_t)220 * 1024) stagesTs--;
+    if (stagesTs >= 3 && !(g && g[0] == 's' && g[1] == 's')) {
+      TcTsParams q{};
+      q.Y = Y; q.ldY = ldY; q.rows = rows; q.outDim = outDim; q.BN = BN; q.numKb = Kpad / TC_BK;
+      q.stages = stagesTs; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
+      q.relu = relu; q.rowEnd = rowEnd; q.colLeft = colLeft;
+      { const char* e = getenv("ROC_TS_SPLIT"); q.splitGroups = (e && e[0] == '1') ? 1 : 2; }
+      const size_t smemTs = (size_t)stagesTs * stageBytesTs + 1024 + 256;
+      static size_t configuredTs = 0;
+      if (smemTs > configuredTs) {
+        ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemTs));
+        configuredTs = smemTs;
+      }
+      k_tc_linear_fwd_ts<<<grid, 256 + 128 * q.splitGroups, smemTs, st>>>(mapX, mapWhi, mapWlo, q);
+      ROC_LAUNCH_CHECK();
+      return ROC_OK;
+    }
+  }
+
   TcFwdParams p{};
   p.Y = Y; p.ldY = ldY; p.rows = rows; p.outDim = outDim; p.BN = BN; p.numKb = Kpad / TC_BK;
   p.relu = relu; p.rowEnd = rowEnd; p.colLeft = colLeft;
@@ -237,9 +463,6 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
     ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     configured = smemBytes;
   }
-  const int64_t numTiles = (rows + TC_BM - 1) / TC_BM;
-  int grid = sm_count();
-  if (numTiles < grid) grid = (int)numTiles;
   k_tc_linear_fwd<<<grid, TC_THREADS, smemBytes, st>>>(mapX, mapWhi, mapWlo, p);
   ROC_LAUNCH_CHECK();
   return ROC_OK;

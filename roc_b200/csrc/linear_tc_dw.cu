@@ -176,6 +176,199 @@ k_tc_linear_dw(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
 }
 
+// ---------------------------------------------------------------------------
+// TS variant: X^T reaches the tensor core through TMEM (A operand, K-major: lane =
+// X column i, TMEM column = vertex), so the X tile crosses shared memory once (TMA in,
+// one transposing read by the split warps) instead of five times.  Only the small
+// dY tile is split hi/lo in shared memory (B operand, MN-major, as above).
+//   stage  = KS (16) vertices: G boxes [16 x 128] of X (no swizzle) + dY atoms
+//   A slot = one M-tile of one stage: 16 hi + 16 lo TMEM columns, ring of 6 slots
+//   TMEM   = G accumulators [128 x BN] (<= 320 columns) + 192 columns of A slots
+constexpr int DWT_KS = 16;
+constexpr int DWT_SLOTS = 6;
+constexpr int DWT_MAX_STAGES = 4;
+
+struct TcDwTsParams {
+  float* ws; int64_t rows; int inDim, outDim, BN, nbAtoms, G, MT;
+  int64_t vPerSplit;       // multiple of DWT_KS
+  uint32_t tmemCols, aCol0;
+  int stages;
+  int splitGroups;         // 1 or 2 warpgroups of split warps (alternate A slots)
+};
+
+__global__ void __launch_bounds__(384, 1)
+k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                  const TcDwTsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int g0 = blockIdx.y * p.G;
+  const int nt = min(p.G, p.MT - g0);
+  const uint32_t xTile = DWT_KS * DW_BM * 4;                         // 8 KB per M-tile
+  const uint32_t xBytes = (uint32_t)p.G * xTile;
+  const uint32_t bBytes = (uint32_t)p.nbAtoms * 1024u * (DWT_KS / 8);  // raw dY (later hi), lo beside it
+  const uint32_t stageBytes = xBytes + 2 * bBytes;
+  uint8_t* barBase = smem + (size_t)p.stages * stageBytes;
+  uint64_t* fullTma = reinterpret_cast<uint64_t*>(barBase);          // [stages]
+  uint64_t* bFull = fullTma + DWT_MAX_STAGES;                        // [stages] dY hi/lo ready in smem
+  uint64_t* empty = bFull + DWT_MAX_STAGES;                          // [stages] stage's MMAs retired
+  uint64_t* aFull = empty + DWT_MAX_STAGES;                          // [slots] X^T hi/lo stored to TMEM
+  uint64_t* aEmpty = aFull + DWT_SLOTS;                              // [slots] MMAs done with the slot
+  uint64_t* tmemFull = aEmpty + DWT_SLOTS;
+  uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(tmemFull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t v0 = (int64_t)blockIdx.x * p.vPerSplit;
+  const int64_t v1 = min(p.rows, v0 + p.vPerSplit);
+  const int numSteps = (v1 > v0) ? (int)((v1 - v0 + DWT_KS - 1) / DWT_KS) : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapDY);
+    for (int s = 0; s < p.stages; s++) { mbar_init(&fullTma[s], 1); mbar_init(&bFull[s], 4); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < DWT_SLOTS; a++) { mbar_init(&aFull[a], 4); mbar_init(&aEmpty[a], 1); }
+    mbar_init(tmemFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmemAddr, p.tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemAddr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)nt * xTile + bBytes;
+      for (int step = 0; step < numSteps; step++) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stageBytes;
+        mbar_arrive_expect_tx(&fullTma[s], tx);
+        const int v = (int)(v0 + (int64_t)step * DWT_KS);
+        for (int j = 0; j < nt; j++) tma_load_2d(st + (size_t)j * xTile, &mapX, (g0 + j) * DW_BM, v, &fullTma[s]);
+        for (int ks = 0; ks < DWT_KS / 8; ks++)
+          for (int b = 0; b < p.nbAtoms; b++)
+            tma_load_2d(st + xBytes + (size_t)(ks * p.nbAtoms + b) * 1024, &mapDY, b * 32, v + ks * 8, &fullTma[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer =================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(DW_BM, p.BN, 0, 1);    // A K-major (TMEM), B MN-major
+      int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+      for (int step = 0; step < numSteps; step++) {
+        mbar_wait(&bFull[s], ph);
+        const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + xBytes;
+        const uint32_t bLo = bHi + bBytes;
+        for (int j = 0; j < nt; j++) {
+          mbar_wait(&aFull[a], aph);
+          tc_fence_after();
+          const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)a * 32u;
+          const uint32_t aLo = aHi + 16u;
+          const uint32_t d = tmemBase + (uint32_t)(j * p.BN);
+#pragma unroll
+          for (int ks = 0; ks < DWT_KS / 8; ks++) {
+            const uint32_t off = (uint32_t)(ks * p.nbAtoms) * 1024u;
+            const uint64_t dBh = make_sdesc(bHi + off, 1024u, 512u, 1u), dBl = make_sdesc(bLo + off, 1024u, 512u, 1u);
+            umma_tf32_ts(d, aLo + ks * 8, dBh, idesc, (step > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_ts(d, aHi + ks * 8, dBl, idesc, 1u);
+            umma_tf32_ts(d, aHi + ks * 8, dBh, idesc, 1u);
+          }
+          umma_commit(&aEmpty[a]);
+          if (++a == DWT_SLOTS) { a = 0; aph ^= 1; }
+        }
+        umma_commit(&empty[s]);
+        if (step == numSteps - 1) umma_commit(tmemFull);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============ dY split (smem), X^T split (TMEM), then the epilogue ============
+    // split group g takes every splitGroups-th A slot (flattened over steps x M-tiles); the
+    // group that owns a step's first slot also splits that step's dY tile
+    const int g = (warp - 4) >> 2;
+    const int t = (threadIdx.x - 128) & 127;   // X column inside the M-tile == TMEM lane
+    const uint32_t laneBase = (uint32_t)((warp & 3) * 32) << 16;
+    const int nB4 = (int)(bBytes / 16);
+    const int64_t iters = (int64_t)numSteps * nt;
+    int lastStep = -1;
+    for (int64_t it = g; it < iters; it += p.splitGroups) {
+      const int step = (int)(it / nt), j = (int)(it - (int64_t)step * nt);
+      const int s = step % p.stages;
+      const int a = (int)(it % DWT_SLOTS);
+      const uint32_t aph = (uint32_t)((it / DWT_SLOTS) & 1);
+      uint8_t* st = smem + (size_t)s * stageBytes;
+      if (step != lastStep) {
+        lastStep = step;
+        mbar_wait(&fullTma[s], (uint32_t)((step / p.stages) & 1));
+        if (((int64_t)step * nt) % p.splitGroups == g) {
+          float4* b = reinterpret_cast<float4*>(st + xBytes);
+          float4* bl = reinterpret_cast<float4*>(st + xBytes + bBytes);
+          for (int i = t; i < nB4; i += 128) {
+            float4 v = b[i], h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            b[i] = h; bl[i] = l;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bFull[s]);
+        }
+      }
+      const float* x = reinterpret_cast<const float*>(st + (size_t)j * xTile) + t;   // [KS][128]: column t
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < DWT_KS; k++) {
+        const float e = x[k * DW_BM];
+        const uint32_t h = __float_as_uint(e) & 0xFFFFE000u;
+        hi[k] = h;
+        lo[k] = __float_as_uint(e - __uint_as_float(h));
+      }
+      mbar_wait(&aEmpty[a], aph ^ 1);
+      tc_fence_after();
+      const uint32_t taddr = tmemBase + laneBase + p.aCol0 + (uint32_t)a * 32u;
+      tmem_st16(taddr, hi);
+      tmem_st16(taddr + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aFull[a]);
+    }
+    if (g == 0) {
+    // ---- epilogue: D_j[i_local][o] -> ws[split][o*inDim + i]  (lane = i_local: coalesced along i)
+    float* ws = p.ws + (size_t)blockIdx.x * ((size_t)p.inDim * p.outDim);
+    if (numSteps > 0) {
+      mbar_wait(tmemFull, 0);
+      tc_fence_after();
+    }
+    for (int j = 0; j < nt; j++) {
+      const int i = (g0 + j) * DW_BM + (warp - 4) * 32 + lane;
+      const uint32_t taddr = tmemBase + laneBase + (uint32_t)(j * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        if (numSteps > 0) { tmem_ld16(taddr + (uint32_t)c0, r); tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int k = 0; k < 16; k++) r[k] = 0u;
+        }
+        if (i < p.inDim) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const int o = c0 + k;
+            if (o < p.outDim) ws[(size_t)o * p.inDim + i] = __uint_as_float(r[k]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
+}
+
 __global__ void __launch_bounds__(256)
 k_tc_splitk_reduce(int64_t count, int splits, const float* __restrict__ part, float* __restrict__ dW) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
@@ -185,13 +378,35 @@ k_tc_splitk_reduce(int64_t count, int splits, const float* __restrict__ part, fl
   }
 }
 
-struct DwPlan { int BN, nb, G, MT, groups, splits, stages; size_t stageBytes; };
+struct DwPlan { int BN, nb, G, MT, groups, splits, stages; size_t stageBytes; bool ts; };
 
 static int tc_dw_plan(int64_t rows, int inDim, int outDim, DwPlan* q) {
   if (outDim > 256 || outDim < 1 || inDim < 4 || rows < 8) return ROC_ERR_UNSUPPORTED;
   q->BN = (outDim + 15) / 16 * 16;
   q->nb = (outDim + 31) / 32;
   q->MT = (inDim + DW_BM - 1) / DW_BM;
+  {
+    // TS plan: accumulators in <= 320 TMEM columns, 192 columns of A slots
+    const char* e = getenv("ROC_B200_GEMM");
+    int g = 320 / q->BN;
+    if (g > q->MT) g = q->MT;
+    if (g >= 1 && !(e && e[0] == 's' && e[1] == 's')) {
+      q->ts = true;
+      q->G = g;
+      q->groups = (q->MT + g - 1) / g;
+      q->stageBytes = (size_t)g * DWT_KS * DW_BM * 4 + (size_t)2 * q->nb * 1024 * (DWT_KS / 8);
+      int st = (int)((200 * 1024) / q->stageBytes);
+      if (st > DWT_MAX_STAGES) st = DWT_MAX_STAGES;
+      q->stages = st;
+      int sp = sm_count() / q->groups;
+      if (sp < 1) sp = 1;
+      int64_t maxSp = (rows + 63) / 64;
+      if (sp > maxSp) sp = (int)maxSp;
+      q->splits = sp;
+      if (st >= 2) return ROC_OK;
+    }
+    q->ts = false;
+  }
   int g = 512 / q->BN;
   if (g > q->MT) g = q->MT;
   // shared memory per stage: 2 * (G * 4 KB + nb KB); want >= 3 stages in ~200 KB
@@ -226,6 +441,30 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
   const size_t count = (size_t)inDim * outDim;
   if (wsBytes < (size_t)q.splits * count * sizeof(float)) return ROC_ERR_INVALID;
   CUtensorMap mapX, mapDY;
+  if (q.ts) {
+    if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, DWT_KS, DW_BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return ROC_ERR_UNSUPPORTED;
+    if (!make_tmap_f32_2d(&mapDY, dY, (uint64_t)rows, (uint64_t)outDim, (uint64_t)ldDY, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
+    TcDwTsParams t{};
+    t.ws = workspace; t.rows = rows; t.inDim = inDim; t.outDim = outDim; t.BN = q.BN; t.nbAtoms = q.nb; t.G = q.G;
+    t.MT = q.MT; t.stages = q.stages;
+    t.vPerSplit = ((rows + q.splits - 1) / q.splits + DWT_KS - 1) / DWT_KS * DWT_KS;
+    t.tmemCols = 512; t.aCol0 = 320;
+    { const char* e = getenv("ROC_TS_SPLIT"); t.splitGroups = (e && e[0] == '1') ? 1 : 2; }
+    const size_t smemTs = (size_t)q.stages * q.stageBytes + 1024 + 256;
+    static size_t configuredTs = 0;
+    if (smemTs > configuredTs) {
+      ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_dw_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemTs));
+      configuredTs = smemTs;
+    }
+    dim3 gridTs((unsigned)q.splits, (unsigned)q.groups, 1);
+    k_tc_linear_dw_ts<<<gridTs, 128 + 128 * t.splitGroups, smemTs, st>>>(mapX, mapDY, t);
+    ROC_LAUNCH_CHECK();
+    int64_t blocksTs = ((int64_t)count + 255) / 256;
+    if (blocksTs > sm_count() * 8) blocksTs = sm_count() * 8;
+    k_tc_splitk_reduce<<<(unsigned)blocksTs, 256, 0, st>>>((int64_t)count, q.splits, workspace, dW);
+    ROC_LAUNCH_CHECK();
+    return ROC_OK;
+  }
   if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
   if (!make_tmap_f32_2d(&mapDY, dY, (uint64_t)rows, (uint64_t)outDim, (uint64_t)ldDY, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
   TcDwParams p{};
