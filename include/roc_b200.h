@@ -207,6 +207,15 @@ int roc_dropout_bwd(int64_t rows, int H, int64_t firstRow, float rate, uint64_t 
                     uint32_t step, const float* dY, int64_t ldDY, float* dX,
                     int64_t ldDX, roc_stream_t stream);
 
+/* The same mask, packed one bit per element: bit (h & 31) of
+ * mask[row * ldMask + (h >> 5)] = keep(firstRow + row, h).  ldMask (32-bit words per
+ * row) must be a multiple of 4 and >= ceil(H/32); words / bits beyond H are written 0.
+ * Feeds roc_linear_fwd_dropout / roc_linear_bwd_dropout, which apply dropout to the
+ * Linear's input while loading it, so the dropped copy of X (dropout_kernel.cu:98's
+ * output tensor) is never written to or re-read from HBM. */
+int roc_dropout_mask(int64_t rows, int H, int64_t firstRow, float rate, uint64_t seed,
+                     uint32_t step, uint32_t* mask, int64_t ldMask, roc_stream_t stream);
+
 /* Replaces SoftmaxCrossEntropy::backward_task, softmax_kernel.cu:81-171:
  * cudnnSoftmaxForward(ACCURATE) -> calc_loss (:41-79) -> softmax_backward
  * (:19-33) in ONE kernel.  `labels` is the one-hot fp32 [rows][ldL] tensor the
@@ -242,12 +251,32 @@ int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t 
  *   dX[v][i] (+)= sum_o W[o*inDim+i] * dY[v][o]       (:227-231) — skipped when
  *   dX == NULL (leaf input, quirk Q8); accumulate_dX selects += vs =.
  * `workspace` holds split-K partials of dW; size from roc_linear_bwd_workspace_bytes. */
+/* roc_linear_fwd on dropout(X): Y = (keep ? X / (1 - rate) : 0) W^T with `mask` from
+ * roc_dropout_mask (same rate).  Bit-identical to roc_dropout_fwd followed by
+ * roc_linear_fwd.  rate == 0 ignores the mask (infer mode: dropout is a copy,
+ * dropout_kernel.cu:159-180). */
+int roc_linear_fwd_dropout(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                           const float* W, float* Y, int64_t ldY, int activation, int flags,
+                           const roc_eid_t* rowEnd, roc_eid_t colLeft, const uint32_t* mask,
+                           int64_t ldMask, float rate, roc_stream_t stream);
+
 size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int outDim);
 int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
                    const float* W, const float* Y, int64_t ldY, float* dY,
                    int64_t ldDY, float* dW, float* dX, int64_t ldDX,
                    int activation, int accumulate_dX, void* workspace,
                    size_t workspaceBytes, roc_stream_t stream);
+
+/* roc_linear_bwd where the forward input was dropout(X) (X = the tensor BEFORE dropout):
+ * dW uses the masked, scaled X; dX (if non-NULL) is the gradient of the dropout's INPUT,
+ * i.e. cudnnDropoutBackward (dropout_kernel.cu:149-150) applied to the Linear's dX in
+ * the same kernel.  Bit-identical to roc_linear_bwd followed by roc_dropout_bwd. */
+int roc_linear_bwd_dropout(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                           const float* W, const float* Y, int64_t ldY, float* dY,
+                           int64_t ldDY, float* dW, float* dX, int64_t ldDX, int activation,
+                           int accumulate_dX, void* workspace, size_t workspaceBytes,
+                           const uint32_t* mask, int64_t ldMask, float rate,
+                           roc_stream_t stream);
 
 /* ------------------------------------------------------------ optimizer --- */
 

@@ -260,6 +260,9 @@ public:
   int flags;        /* ROC_LINEAR_* (norm epilogue fused) */
   int fwdOut;       /* region the forward writes (-1: own output) */
   int bwdIn;        /* region whose grad feeds backward (-1: own output) */
+  int dropOp;       /* >= 0: layers[dropOp] is the Dropout feeding this op, applied while X is loaded */
+  uint32_t* dropMask;      /* packed keep-mask of that dropout, [rows][dropLd] (roc_dropout_mask) */
+  int64_t dropLd;
 };
 
 class Activation : public GnnOp {  /* gnn.h:287-302, activation.cc */

@@ -201,6 +201,42 @@ k_dropout(int64_t rows, int H, int64_t firstRow, uint32_t thresh, float scale, u
   }
 }
 
+// The same mask as k_dropout, packed: bit b of mask[r][w] = keep(row r, column 32 w + b).
+// One thread builds one word from the 8 (or 9, when the word's first dense index is not a
+// multiple of 4) Philox blocks its 32 elements fall into.  Words beyond ceil(H/32) and bits
+// beyond H are written as zero so whole rows can be fetched blindly.
+__global__ void __launch_bounds__(EW_T)
+k_dropout_mask(int64_t rows, int H, int64_t firstRow, uint32_t thresh, uint32_t seedLo, uint32_t seedHi,
+               uint32_t step, uint32_t* __restrict__ mask, int64_t ldm) {
+  const int Ww = (H + 31) / 32;
+  const int64_t total = rows * ldm;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldm;
+    const int w = (int)(i - r * ldm);
+    uint32_t bits = 0u;
+    if (w < Ww) {
+      const uint64_t k0 = (uint64_t)(firstRow + r) * (uint64_t)H + (uint64_t)(32 * w);
+      const int sh = (int)(k0 & 3);
+      const uint64_t q = k0 >> 2;
+      const int n = min(32, H - 32 * w);
+#pragma unroll
+      for (int b = 0; b < 9; b++) {
+        if (b == 8 && sh == 0) break;
+        const uint64_t qb = q + (uint64_t)b;
+        uint32_t c[4] = {(uint32_t)qb, (uint32_t)(qb >> 32), step, 0u};
+        philox4x32_10(c, seedLo, seedHi);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int j = 4 * b + e - sh;
+          if ((unsigned)j < (unsigned)n && c[e] >= thresh) bits |= 1u << j;
+        }
+      }
+    }
+    mask[i] = bits;
+  }
+}
+
 // --------------------------------------------------- softmax + loss + grad ---
 // One warp per row.  Lanes stride the C columns.  Metrics are reduced per block
 // in shared memory and added to *perf with one atomic per field per block.
@@ -625,6 +661,16 @@ extern "C" int roc_dropout_bwd(int64_t rows, int H, int64_t firstRow, float rate
                                const float* dY, int64_t ldDY, float* dX, int64_t ldDX, roc_stream_t stream) {
   // dX = dY * keep / (1 - rate): the same map as forward (dropout_kernel.cu:149-150)
   return dropout_launch(rows, H, firstRow, rate, seed, step, dY, ldDY, dX, ldDX, as_stream(stream));
+}
+
+extern "C" int roc_dropout_mask(int64_t rows, int H, int64_t firstRow, float rate, uint64_t seed, uint32_t step,
+                                uint32_t* mask, int64_t ldMask, roc_stream_t stream) {
+  if (!mask || rows < 0 || H <= 0 || ldMask < (H + 31) / 32 || rate < 0.f || rate >= 1.f) return ROC_ERR_INVALID;
+  if (rows == 0) return ROC_OK;
+  k_dropout_mask<<<ew_grid(rows * ldMask, EW_T), EW_T, 0, as_stream(stream)>>>(
+      rows, H, firstRow, dropout_thresh(rate), (uint32_t)seed, (uint32_t)(seed >> 32), step, mask, ldMask);
+  ROC_LAUNCH_CHECK();
+  return ROC_OK;
 }
 
 extern "C" int roc_softmax_xent_bwd(int64_t rows, int C, const float* logits, int64_t ldZ, const float* labels,

@@ -255,6 +255,20 @@ bool Model::init(const Config& config) {
       }
     }
   }
+  // ---- fusion of  dropout -> linear  (gnn.cc:79-81, 86-88): the dropout output feeds only the linear
+  if (fuse) {
+    Wiring w = wire(layers);
+    for (size_t l = 0; l < layers.size(); l++) {
+      Dropout* d = as<Dropout>(layers[l]);
+      if (!d || d->fusedInto >= 0) continue;
+      const int ro = d->outputs[0].region;
+      if (w.consumers[ro] != 1) continue;
+      Linear* lin = as<Linear>(layers[w.consumerOp[ro]]);
+      if (!lin || lin->dropOp >= 0 || lin->inputs[0].region != ro) continue;
+      lin->dropOp = (int)l;
+      d->fusedInto = w.consumerOp[ro];
+    }
+  }
   for (size_t l = 0; l < layers.size(); l++) layers[l]->init(*this);
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   return true;
@@ -536,19 +550,51 @@ void InDegreeNorm::backward(const Model& model) {
 
 // ----------------------------------------------------------------- Linear ---
 Linear::Linear(const Model& model, const Tensor& _input, int outDim, ActiMode _activation, Initializer* initializer)
-    : GnnOp(_input), activation(_activation), flags(0), fwdOut(-1), bwdIn(-1) {
+    : GnnOp(_input), activation(_activation), flags(0), fwdOut(-1), bwdIn(-1), dropOp(-1), dropMask(nullptr), dropLd(0) {
   ROC_ASSERT(_input.numDim == 2);   // linear.cc:41-42
   ROC_ASSERT(_input.dims[1] == model.myGraph.numNodes);
   weight = model.create_weight_tensor((int)_input.dims[0], outDim, initializer);
   numOutputs = 1;
   outputs[0] = model.create_node_tensor<DATATYPE>(outDim);
 }
-void Linear::init(const Model&) {}
+void Linear::init(const Model& model) {
+  if (dropOp < 0) return;
+  RuntimeImpl* rt = model.ctx;
+  dropLd = (((int64_t)weight.dims[0] + 31) / 32 + 3) / 4 * 4;
+  dropMask = (uint32_t*)rt->dmalloc((size_t)std::max<int64_t>(model.local_rows(), 1) * (size_t)dropLd * sizeof(uint32_t));
+}
+
+namespace {
+// the Dropout folded into a Linear: its rate in the current mode and its Philox key
+struct FusedDrop { const Dropout* op; float rate; uint64_t key; int inRegion; };
+FusedDrop fused_drop(const Model& model, int dropOp) {
+  const Dropout* d = static_cast<const Dropout*>(model.layers[(size_t)dropOp]);
+  FusedDrop f;
+  f.op = d;
+  f.rate = (model.mode == MD_MODE_TRAIN) ? d->rate : 0.0f;    // infer: dropout is a copy (dropout_kernel.cu:159-180)
+  f.key = ((uint64_t)(uint32_t)d->seed << 32) | (uint32_t)d->opIndex;
+  f.inRegion = d->inputs[0].region;
+  return f;
+}
+}  // namespace
 
 void Linear::forward(const Model& model) {
   RuntimeImpl* rt = model.ctx;
   const Graph& g = model.myGraph;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
+  if (dropOp >= 0) {
+    // dropout -> linear: the mask is generated packed (1 bit / element) and applied while the GEMM
+    // loads X, so the dropped copy of X is never materialised
+    const FusedDrop f = fused_drop(model, dropOp);
+    if (f.rate > 0.0f)
+      ROC_CHECK(roc_dropout_mask(model.local_rows(), (int)weight.dims[0], g.rowLeft, f.rate, f.key, rt->trainStep,
+                                 dropMask, dropLd, rt->stream));
+    ROC_CHECK(roc_linear_fwd_dropout(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1],
+                                     rt->data(f.inRegion), rt->t(f.inRegion).ld, rt->data(weight.region),
+                                     rt->data(outRegion), rt->t(outRegion).ld, (int)activation, flags, g.d_rowEnd,
+                                     g.colLeft, dropMask, dropLd, f.rate, rt->stream));
+    return;
+  }
   ROC_CHECK(roc_linear_fwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
                            rt->t(inputs[0].region).ld, rt->data(weight.region), rt->data(outRegion),
                            rt->t(outRegion).ld, (int)activation, flags, g.d_rowEnd, g.colLeft, rt->stream));
@@ -557,8 +603,21 @@ void Linear::forward(const Model& model) {
 void Linear::backward(const Model& model) {
   RuntimeImpl* rt = model.ctx;
   const int gy = bwdIn >= 0 ? bwdIn : outputs[0].region;
-  float* dX = rt->t(inputs[0].region).requiresGrad ? rt->grad(inputs[0].region) : NULL;   // Q8: leaf grads skipped
   const float* Y = (activation != AC_MODE_NONE) ? rt->data(outputs[0].region) : NULL;
+  if (dropOp >= 0) {
+    // dW from the masked X; dX lands directly in the gradient of the dropout's input (the
+    // dropout backward, dropout_kernel.cu:149-150, runs in the dX epilogue; it always overwrites, :119)
+    const FusedDrop f = fused_drop(model, dropOp);
+    ROC_ASSERT(resetInputGrads[0]);
+    float* dX = rt->t(f.inRegion).requiresGrad ? rt->grad(f.inRegion) : NULL;   // Q8: leaf grads skipped
+    ROC_CHECK(roc_linear_bwd_dropout(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1],
+                                     rt->data(f.inRegion), rt->t(f.inRegion).ld, rt->data(weight.region), Y,
+                                     rt->t(outputs[0].region).ld, rt->grad(gy), rt->t(gy).ld,
+                                     rt->grad(weight.region), dX, rt->t(f.inRegion).ld, (int)activation, 0,
+                                     rt->linWs, rt->linWsBytes, dropMask, dropLd, f.rate, rt->stream));
+    return;
+  }
+  float* dX = rt->t(inputs[0].region).requiresGrad ? rt->grad(inputs[0].region) : NULL;   // Q8: leaf grads skipped
   ROC_CHECK(roc_linear_bwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
                            rt->t(inputs[0].region).ld, rt->data(weight.region), Y, rt->t(outputs[0].region).ld,
                            rt->grad(gy), rt->t(gy).ld, rt->grad(weight.region), dX, rt->t(inputs[0].region).ld,
@@ -626,6 +685,7 @@ Dropout::Dropout(const Model& model, const Tensor& _input, float _rate, int _see
 }
 void Dropout::init(const Model&) {}
 void Dropout::forward(const Model& model) {
+  if (fusedInto >= 0) return;   // applied by the consuming Linear while it loads X
   RuntimeImpl* rt = model.ctx;
   // train: masked scale (dropout_kernel.cu:98-99); infer: plain copy (:159-180)
   const float r = (model.mode == MD_MODE_TRAIN) ? rate : 0.0f;
@@ -638,6 +698,7 @@ void Dropout::backward(const Model& model) {
   RuntimeImpl* rt = model.ctx;
   if (!rt->t(inputs[0].region).requiresGrad) return;   // leaf input (Q8)
   ROC_ASSERT(resetInputGrads[0]);   // dropout_kernel.cu:119
+  if (fusedInto >= 0) return;       // the consuming Linear's dX epilogue already wrote this gradient
   const float r = (model.mode == MD_MODE_TRAIN) ? rate : 0.0f;
   const uint64_t key = ((uint64_t)(uint32_t)seed << 32) | (uint32_t)opIndex;
   ROC_CHECK(roc_dropout_bwd(model.local_rows(), (int)inputs[0].dims[0], model.myGraph.rowLeft, r, key, rt->trainStep,

@@ -6,20 +6,22 @@
 namespace roc {
 int simt_dw_splits(int64_t rows, int inDim, int outDim);
 int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
-                    int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
+                    int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
+                    cudaStream_t st);
 int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                   int64_t ldDX, int accumulate, cudaStream_t st);
+                   int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st);
 int simt_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
-                   float* dW, float* workspace, size_t wsBytes, cudaStream_t st);
+                   float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st);
 int relu_bwd_inplace(int64_t rows, int H, const float* Y, int64_t ldY, float* dY, int64_t ldDY, cudaStream_t st);
 
 // tensor-core path (linear_tc.cu); each returns ROC_ERR_UNSUPPORTED when the
 // shape / alignment is outside what the tcgen05 kernels take.
 int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
-                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
+                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
+                  cudaStream_t st);
 size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim);
 int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
-                 float* dW, float* workspace, size_t wsBytes, cudaStream_t st);
+                 float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st);
 
 // ROC_B200_GEMM=simt forces the exact-fp32 SIMT kernels (used by tests to
 // cross-check the tensor-core path).
@@ -32,9 +34,20 @@ static bool force_simt() {
 
 using namespace roc;
 
-extern "C" int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
-                              float* Y, int64_t ldY, int activation, int flags, const roc_eid_t* rowEnd,
-                              roc_eid_t colLeft, roc_stream_t stream) {
+// A dropout mask is usable when rate in (0, 1); rate == 0 is the identity (infer mode).
+static int mask_args(const uint32_t* mask, int64_t ldMask, float rate, int inDim, DropMask* dm, const DropMask** out) {
+  *out = nullptr;
+  if (rate < 0.f || rate >= 1.f) return ROC_ERR_INVALID;
+  if (rate == 0.f) return ROC_OK;
+  if (!mask || ldMask < (inDim + 31) / 32 || (ldMask % 4)) return ROC_ERR_INVALID;
+  dm->bits = mask; dm->ld = ldMask; dm->scale = 1.0f / (1.0f - rate);   // the scale of roc_dropout_fwd
+  *out = dm;
+  return ROC_OK;
+}
+
+static int linear_fwd_impl(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                           float* Y, int64_t ldY, int activation, int flags, const roc_eid_t* rowEnd,
+                           roc_eid_t colLeft, const DropMask* dm, roc_stream_t stream) {
   if (!X || !W || !Y || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldY < outDim) return ROC_ERR_INVALID;
   if (activation != ROC_AC_MODE_NONE && activation != ROC_AC_MODE_RELU) return ROC_ERR_UNSUPPORTED;  // linear_kernel.cu:96
   if ((flags & ROC_LINEAR_NORM_EPILOGUE) && !rowEnd) return ROC_ERR_INVALID;
@@ -42,10 +55,26 @@ extern "C" int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* 
   const uint64_t* re = (flags & ROC_LINEAR_NORM_EPILOGUE) ? rowEnd : nullptr;
   const int relu = activation == ROC_AC_MODE_RELU;
   if (!force_simt()) {
-    int rc = tc_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, as_stream(stream));
+    int rc = tc_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, dm, as_stream(stream));
     if (rc != ROC_ERR_UNSUPPORTED) return rc;
   }
-  return simt_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, as_stream(stream));
+  return simt_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, dm, as_stream(stream));
+}
+
+extern "C" int roc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                              float* Y, int64_t ldY, int activation, int flags, const roc_eid_t* rowEnd,
+                              roc_eid_t colLeft, roc_stream_t stream) {
+  return linear_fwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, activation, flags, rowEnd, colLeft, nullptr, stream);
+}
+
+extern "C" int roc_linear_fwd_dropout(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                                      const float* W, float* Y, int64_t ldY, int activation, int flags,
+                                      const roc_eid_t* rowEnd, roc_eid_t colLeft, const uint32_t* mask,
+                                      int64_t ldMask, float rate, roc_stream_t stream) {
+  DropMask dm; const DropMask* use;
+  int rc = mask_args(mask, ldMask, rate, inDim, &dm, &use);
+  if (rc != ROC_OK) return rc;
+  return linear_fwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, activation, flags, rowEnd, colLeft, use, stream);
 }
 
 extern "C" size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int outDim) {
@@ -55,10 +84,10 @@ extern "C" size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int ou
   return a > b ? a : b;
 }
 
-extern "C" int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
-                              const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
-                              int64_t ldDX, int activation, int accumulate_dX, void* workspace,
-                              size_t workspaceBytes, roc_stream_t stream) {
+static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                           const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
+                           int64_t ldDX, int activation, int accumulate_dX, void* workspace,
+                           size_t workspaceBytes, const DropMask* dm, roc_stream_t stream) {
   if (!X || !W || !dY || !dW || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldDY < outDim)
     return ROC_ERR_INVALID;
   if (dX && ldDX < inDim) return ROC_ERR_INVALID;
@@ -73,13 +102,33 @@ extern "C" int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* 
   if (!workspace) return ROC_ERR_INVALID;
   int rc = ROC_ERR_UNSUPPORTED;
   if (!force_simt())
-    rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, st);
+    rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
   if (rc == ROC_ERR_UNSUPPORTED)
-    rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, st);
+    rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
   if (rc != ROC_OK) return rc;
   if (dX) {
-    rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, st);
+    rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
     if (rc != ROC_OK) return rc;
   }
   return ROC_OK;
+}
+
+extern "C" int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
+                              const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
+                              int64_t ldDX, int activation, int accumulate_dX, void* workspace,
+                              size_t workspaceBytes, roc_stream_t stream) {
+  return linear_bwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, dY, ldDY, dW, dX, ldDX, activation, accumulate_dX,
+                         workspace, workspaceBytes, nullptr, stream);
+}
+
+extern "C" int roc_linear_bwd_dropout(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
+                                      const float* W, const float* Y, int64_t ldY, float* dY, int64_t ldDY,
+                                      float* dW, float* dX, int64_t ldDX, int activation, int accumulate_dX,
+                                      void* workspace, size_t workspaceBytes, const uint32_t* mask,
+                                      int64_t ldMask, float rate, roc_stream_t stream) {
+  DropMask dm; const DropMask* use;
+  int rc = mask_args(mask, ldMask, rate, inDim, &dm, &use);
+  if (rc != ROC_OK) return rc;
+  return linear_bwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, dY, ldDY, dW, dX, ldDX, activation, accumulate_dX,
+                         workspace, workspaceBytes, use, stream);
 }

@@ -26,6 +26,9 @@ struct GemmP {
   int relu;               // epilogue relu
   const uint64_t* rowEnd; // epilogue row scale 1/sqrtf(deg(m)) if non-NULL
   uint64_t colLeft;
+  // fused dropout (NULL = none): maskOn 1 = A element (m, k) [fwd], 2 = B element (k, n) [dW],
+  // 3 = C element (m, n) [dX: the dropout backward]
+  const uint32_t* mask; int64_t ldm; float mscale; int maskOn;
 };
 
 template <bool A_KCONTIG, bool B_KCONTIG>
@@ -54,7 +57,10 @@ k_sgemm(const GemmP p) {
       if (A_KCONTIG) { kk = lin % GB_K; mm = lin / GB_K; } else { mm = lin % GB_M; kk = lin / GB_M; }
       int64_t m = m0 + mm, k = k0 + kk;
       float v = 0.f;
-      if (m < p.M && k < kEnd) v = A_KCONTIG ? p.A[m * p.lda + k] : p.A[k * p.lda + m];
+      if (m < p.M && k < kEnd) {
+        v = A_KCONTIG ? p.A[m * p.lda + k] : p.A[k * p.lda + m];
+        if (p.maskOn == 1) v = drop_apply(p.mask, p.ldm, p.mscale, m, (int)k, v);
+      }
       As[kk][mm] = v;
     }
 #pragma unroll
@@ -64,7 +70,10 @@ k_sgemm(const GemmP p) {
       if (B_KCONTIG) { kk = lin % GB_K; nn = lin / GB_K; } else { nn = lin % GB_N; kk = lin / GB_N; }
       int n = n0 + nn; int64_t k = k0 + kk;
       float v = 0.f;
-      if (n < p.N && k < kEnd) v = B_KCONTIG ? p.B[(int64_t)n * p.ldb + k] : p.B[k * p.ldb + n];
+      if (n < p.N && k < kEnd) {
+        v = B_KCONTIG ? p.B[(int64_t)n * p.ldb + k] : p.B[k * p.ldb + n];
+        if (p.maskOn == 2) v = drop_apply(p.mask, p.ldm, p.mscale, k, n, v);
+      }
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -99,6 +108,7 @@ k_sgemm(const GemmP p) {
       float v = acc[i][j];
       if (p.relu) v = relu_nanprop(v);   // reference order: sgemm -> relu (linear_kernel.cu:83-104)
       if (p.rowEnd) v = v / d;           // then the model's indegree_norm (gnn.cc:82)
+      if (p.maskOn == 3) v = drop_apply(p.mask, p.ldm, p.mscale, m, n, v);
       float* dst = C + m * p.ldc + n;
       *dst = p.accumulate ? *dst + v : v;
     }
@@ -137,12 +147,19 @@ int simt_dw_splits(int64_t rows, int inDim, int outDim) {
   return want;
 }
 
+static void set_mask(GemmP& p, const DropMask* dm, int on) {
+  if (!dm) return;
+  p.mask = dm->bits; p.ldm = dm->ld; p.mscale = dm->scale; p.maskOn = on;
+}
+
 int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
-                    int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st) {
+                    int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
+                    cudaStream_t st) {
   GemmP p{};
   p.A = X; p.lda = ldX; p.B = W; p.ldb = inDim; p.C = Y; p.ldc = ldY;
   p.M = rows; p.N = outDim; p.K = inDim; p.kPerSplit = inDim; p.splitStrideC = 0;
   p.accumulate = 0; p.relu = relu; p.rowEnd = rowEnd; p.colLeft = colLeft;
+  set_mask(p, dm, 1);
   dim3 grid((unsigned)((rows + GB_M - 1) / GB_M), (unsigned)((outDim + GB_N - 1) / GB_N), 1);
   k_sgemm<true, true><<<grid, G_THREADS, 0, st>>>(p);
   ROC_LAUNCH_CHECK();
@@ -150,10 +167,11 @@ int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t
 }
 
 int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                   int64_t ldDX, int accumulate, cudaStream_t st) {
+                   int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st) {
   GemmP p{};
   p.A = dY; p.lda = ldDY; p.B = W; p.ldb = inDim; p.C = dX; p.ldc = ldDX;
   p.M = rows; p.N = inDim; p.K = outDim; p.kPerSplit = outDim; p.accumulate = accumulate;
+  set_mask(p, dm, 3);
   dim3 grid((unsigned)((rows + GB_M - 1) / GB_M), (unsigned)((inDim + GB_N - 1) / GB_N), 1);
   k_sgemm<true, false><<<grid, G_THREADS, 0, st>>>(p);
   ROC_LAUNCH_CHECK();
@@ -161,7 +179,7 @@ int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t
 }
 
 int simt_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
-                   float* dW, float* workspace, size_t wsBytes, cudaStream_t st) {
+                   float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st) {
   int splits = simt_dw_splits(rows, inDim, outDim);
   int64_t count = (int64_t)inDim * outDim;
   if (wsBytes < (size_t)splits * count * sizeof(float)) return ROC_ERR_INVALID;
@@ -170,6 +188,7 @@ int simt_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t 
   p.M = outDim; p.N = inDim; p.K = rows;
   p.kPerSplit = ((rows + splits - 1) / splits + GB_K - 1) / GB_K * GB_K;
   p.splitStrideC = count; p.accumulate = 0;
+  set_mask(p, dm, 2);
   dim3 grid((unsigned)((outDim + GB_M - 1) / GB_M), (unsigned)((inDim + GB_N - 1) / GB_N), (unsigned)splits);
   k_sgemm<false, false><<<grid, G_THREADS, 0, st>>>(p);
   ROC_LAUNCH_CHECK();

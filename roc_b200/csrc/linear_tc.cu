@@ -214,6 +214,7 @@ struct TcTsParams {
   int64_t rows; int outDim; int BN; int numKb; int stages;
   uint32_t tmemCols, dStride, aCol0;
   int splitGroups;      // 1 or 2 warpgroups of split warps (alternate k-blocks)
+  const uint32_t* mask; int64_t ldm; float mscale;   // fused dropout of X (NULL = none)
   int relu;
   const uint64_t* rowEnd; uint64_t colLeft;
 };
@@ -269,7 +270,7 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   uint64_t* dEmpty = dFull + 2;                             // [2] accumulator drained by the epilogue
   uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(dEmpty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t numTiles = (p.rows + TC_BM - 1) / TC_BM;
 
   if (threadIdx.x == 0) {
@@ -286,38 +287,40 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.numKb; kb++) {
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = smem + (size_t)s * stageBytes;
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.numKb; kb++) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stageBytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], aBytes + 2 * bBytes);
           tma_load_2d(st, &mapX, kb * TC_BK, (int)(tile * TC_BM), &full[s]);
           tma_load_2d(st + aBytes, &mapWhi, kb * TC_BK, 0, &full[s]);
           tma_load_2d(st + aBytes + bBytes, &mapWlo, kb * TC_BK, 0, &full[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================= MMA issuer =================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN, 0, 0);
-      int s = 0; uint32_t ph = 0; uint32_t tl = 0;
-      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, tl++) {
-        const uint32_t b = tl & 1u;
-        mbar_wait(&dEmpty[b], ((tl >> 1) & 1u) ^ 1u);   // the epilogue has drained accumulator b
+    // the whole warp runs the loop converged; one elected lane issues (see elect_one)
+    const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN, 0, 0);
+    int s = 0; uint32_t ph = 0; uint32_t tl = 0;
+    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, tl++) {
+      const uint32_t b = tl & 1u;
+      mbar_wait(&dEmpty[b], ((tl >> 1) & 1u) ^ 1u);   // the epilogue has drained accumulator b
+      tc_fence_after();
+      const uint32_t dAddr = tmemBase + b * p.dStride;
+      for (int kb = 0; kb < p.numKb; kb++) {
+        mbar_wait(&full[s], ph);                      // W tiles landed
+        mbar_wait(&aFull[s], ph);                     // X hi/lo stored to TMEM slot s
         tc_fence_after();
-        const uint32_t dAddr = tmemBase + b * p.dStride;
-        for (int kb = 0; kb < p.numKb; kb++) {
-          mbar_wait(&full[s], ph);                      // W tiles landed
-          mbar_wait(&aFull[s], ph);                     // X hi/lo stored to TMEM slot s
-          tc_fence_after();
-          const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)s * 64u;
-          const uint32_t aLo = aHi + 32u;
-          const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + aBytes;
-          const uint32_t bLo = bHi + bBytes;
+        const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)s * 64u;
+        const uint32_t aLo = aHi + 32u;
+        const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + aBytes;
+        const uint32_t bLo = bHi + bBytes;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UK; k++) {
             const uint32_t off = k * TC_UK * 4;   // bytes along K inside the swizzled row
@@ -328,8 +331,9 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
           }
           umma_commit(&empty[s]);                           // smem stage + TMEM slot reusable
           if (kb == p.numKb - 1) umma_commit(&dFull[b]);   // accumulator of this tile complete
-          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * p.splitGroups) {
@@ -341,9 +345,16 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const uint32_t laneBase = (uint32_t)((warp & 3) * 32) << 16;
     const int64_t myTiles = (numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t iters = myTiles * p.numKb;
+    const bool masked = p.mask != nullptr;
+    int s = g % p.stages; uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+    int kb = g % p.numKb; int64_t tile = blockIdx.x + (int64_t)(g / p.numKb) * gridDim.x;
     for (int64_t it = g; it < iters; it += p.splitGroups) {
-      const int s = (int)(it % p.stages);
-      const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+      // dropout fused into the operand load: bit c of mask[row][kb] keeps column 32 kb + c
+      uint32_t mw = 0xFFFFFFFFu;
+      if (masked) {
+        const int64_t row = tile * TC_BM + t;
+        mw = (row < p.rows) ? __ldg(p.mask + row * p.ldm + kb) : 0u;
+      }
       mbar_wait(&full[s], ph);
       // 128B swizzle: 16-byte chunk j of row t sits at chunk j ^ (t & 7)
       const float4* xr = reinterpret_cast<const float4*>(smem + (size_t)s * stageBytes) + t * 8;
@@ -357,9 +368,11 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
           const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const uint32_t h = __float_as_uint(e[k]) & 0xFFFFE000u;
+            float x = e[k];
+            if (masked) x = ((mw >> (half * 16 + j * 4 + k)) & 1u) ? x * p.mscale : 0.f;   // == k_dropout
+            const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
             hi[j * 4 + k] = h;
-            lo[j * 4 + k] = __float_as_uint(e[k] - __uint_as_float(h));
+            lo[j * 4 + k] = __float_as_uint(x - __uint_as_float(h));
           }
         }
         tmem_st16(taddr + half * 16, hi);
@@ -369,6 +382,8 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aFull[s]);
+      s += p.splitGroups; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      kb += p.splitGroups; while (kb >= p.numKb) { kb -= p.numKb; tile += gridDim.x; }
     }
   } else if (warp >= 4 + 4 * p.splitGroups) {
     // ===== epilogue: TMEM lane = row of the tile; this warp owns lanes 32*(warp%4)..+31 =====
@@ -394,7 +409,8 @@ static float* g_wsplit = nullptr;
 static size_t g_wsplitFloats = 0;
 
 int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
-                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st) {
+                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
+                  cudaStream_t st) {
   if (outDim > 256 || inDim < 8 || rows < 1) return ROC_ERR_UNSUPPORTED;
   if ((ldX % 4) || (ldY % 4) || !aligned16(X) || !aligned16(Y)) return ROC_ERR_UNSUPPORTED;
   if (rows > 0x7FFFFF00ll) return ROC_ERR_UNSUPPORTED;   // TMA coordinates are int32
@@ -434,6 +450,7 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
       q.stages = stagesTs; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
       q.relu = relu; q.rowEnd = rowEnd; q.colLeft = colLeft;
       { const char* e = getenv("ROC_TS_SPLIT"); q.splitGroups = (e && e[0] == '1') ? 1 : 2; }
+      if (dm) { q.mask = dm->bits; q.ldm = dm->ld; q.mscale = dm->scale; }
       const size_t smemTs = (size_t)stagesTs * stageBytesTs + 1024 + 256;
       static size_t configuredTs = 0;
       if (smemTs > configuredTs) {
@@ -446,6 +463,7 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
     }
   }
 
+  if (dm) return ROC_ERR_UNSUPPORTED;   // only the TS kernel fuses the dropout mask
   TcFwdParams p{};
   p.Y = Y; p.ldY = ldY; p.rows = rows; p.outDim = outDim; p.BN = BN; p.numKb = Kpad / TC_BK;
   p.relu = relu; p.rowEnd = rowEnd; p.colLeft = colLeft;

@@ -194,6 +194,7 @@ struct TcDwTsParams {
   uint32_t tmemCols, aCol0;
   int stages;
   int splitGroups;         // 1 or 2 warpgroups of split warps (alternate A slots)
+  const uint32_t* mask; int64_t ldm; float mscale;   // fused dropout of X (NULL = none)
 };
 
 __global__ void __launch_bounds__(384, 1)
@@ -216,7 +217,7 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   uint64_t* tmemFull = aEmpty + DWT_SLOTS;
   uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(tmemFull + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t v0 = (int64_t)blockIdx.x * p.vPerSplit;
   const int64_t v1 = min(p.rows, v0 + p.vPerSplit);
   const int numSteps = (v1 > v0) ? (int)((v1 - v0 + DWT_KS - 1) / DWT_KS) : 0;
@@ -236,36 +237,38 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)nt * xTile + bBytes;
-      for (int step = 0; step < numSteps; step++) {
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * stageBytes;
+    int s = 0; uint32_t ph = 0;
+    const uint32_t tx = (uint32_t)nt * xTile + bBytes;
+    for (int step = 0; step < numSteps; step++) {
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* st = smem + (size_t)s * stageBytes;
+      const int v = (int)(v0 + (int64_t)step * DWT_KS);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&fullTma[s], tx);
-        const int v = (int)(v0 + (int64_t)step * DWT_KS);
         for (int j = 0; j < nt; j++) tma_load_2d(st + (size_t)j * xTile, &mapX, (g0 + j) * DW_BM, v, &fullTma[s]);
         for (int ks = 0; ks < DWT_KS / 8; ks++)
           for (int b = 0; b < p.nbAtoms; b++)
             tma_load_2d(st + xBytes + (size_t)(ks * p.nbAtoms + b) * 1024, &mapDY, b * 32, v + ks * 8, &fullTma[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ================================= MMA issuer =================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(DW_BM, p.BN, 0, 1);    // A K-major (TMEM), B MN-major
-      int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
-      for (int step = 0; step < numSteps; step++) {
-        mbar_wait(&bFull[s], ph);
-        const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + xBytes;
-        const uint32_t bLo = bHi + bBytes;
-        for (int j = 0; j < nt; j++) {
-          mbar_wait(&aFull[a], aph);
-          tc_fence_after();
-          const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)a * 32u;
-          const uint32_t aLo = aHi + 16u;
-          const uint32_t d = tmemBase + (uint32_t)(j * p.BN);
+    // the whole warp runs the loop converged; one elected lane issues (see elect_one)
+    const uint32_t idesc = make_idesc_tf32(DW_BM, p.BN, 0, 1);    // A K-major (TMEM), B MN-major
+    int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+    for (int step = 0; step < numSteps; step++) {
+      mbar_wait(&bFull[s], ph);
+      const uint32_t bHi = smem_u32(smem + (size_t)s * stageBytes) + xBytes;
+      const uint32_t bLo = bHi + bBytes;
+      for (int j = 0; j < nt; j++) {
+        mbar_wait(&aFull[a], aph);
+        tc_fence_after();
+        const uint32_t aHi = tmemBase + p.aCol0 + (uint32_t)a * 32u;
+        const uint32_t aLo = aHi + 16u;
+        const uint32_t d = tmemBase + (uint32_t)(j * p.BN);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < DWT_KS / 8; ks++) {
             const uint32_t off = (uint32_t)(ks * p.nbAtoms) * 1024u;
@@ -275,12 +278,15 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             umma_tf32_ts(d, aHi + ks * 8, dBh, idesc, 1u);
           }
           umma_commit(&aEmpty[a]);
-          if (++a == DWT_SLOTS) { a = 0; aph ^= 1; }
+          if (j == nt - 1) {
+            umma_commit(&empty[s]);
+            if (step == numSteps - 1) umma_commit(tmemFull);
+          }
         }
-        umma_commit(&empty[s]);
-        if (step == numSteps - 1) umma_commit(tmemFull);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        __syncwarp();
+        if (++a == DWT_SLOTS) { a = 0; aph ^= 1; }
       }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 4) {
     // ============ dY split (smem), X^T split (TMEM), then the epilogue ============
@@ -292,16 +298,24 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int nB4 = (int)(bBytes / 16);
     const int64_t iters = (int64_t)numSteps * nt;
     int lastStep = -1;
+    const bool masked = p.mask != nullptr;
+    int step = g / nt, j = g % nt;
+    int s = step % p.stages; uint32_t sph = (uint32_t)(step / p.stages) & 1u;
+    int a = g % DWT_SLOTS; uint32_t aph = 0;
     for (int64_t it = g; it < iters; it += p.splitGroups) {
-      const int step = (int)(it / nt), j = (int)(it - (int64_t)step * nt);
-      const int s = step % p.stages;
-      const int a = (int)(it % DWT_SLOTS);
-      const uint32_t aph = (uint32_t)((it / DWT_SLOTS) & 1);
       uint8_t* st = smem + (size_t)s * stageBytes;
+      // dropout fused into the operand load: this warp's 32 X columns are one mask word per vertex
+      uint32_t mk[DWT_KS];
+      if (masked) {
+        const int64_t v = v0 + (int64_t)step * DWT_KS;
+        const uint32_t* mrow = p.mask + (int64_t)((g0 + j) * 4 + (warp & 3));
+#pragma unroll
+        for (int k = 0; k < DWT_KS; k++) mk[k] = __ldg(mrow + min(v + k, p.rows - 1) * p.ldm);
+      }
       if (step != lastStep) {
         lastStep = step;
-        mbar_wait(&fullTma[s], (uint32_t)((step / p.stages) & 1));
-        if (((int64_t)step * nt) % p.splitGroups == g) {
+        mbar_wait(&fullTma[s], sph);
+        if (j < p.splitGroups && (it - j) % p.splitGroups == g) {   // owner of the step's slot 0
           float4* b = reinterpret_cast<float4*>(st + xBytes);
           float4* bl = reinterpret_cast<float4*>(st + xBytes + bBytes);
           for (int i = t; i < nB4; i += 128) {
@@ -321,7 +335,8 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int k = 0; k < DWT_KS; k++) {
-        const float e = x[k * DW_BM];
+        float e = x[k * DW_BM];
+        if (masked) e = ((mk[k] >> lane) & 1u) ? e * p.mscale : 0.f;   // == k_dropout
         const uint32_t h = __float_as_uint(e) & 0xFFFFE000u;
         hi[k] = h;
         lo[k] = __float_as_uint(e - __uint_as_float(h));
@@ -335,6 +350,9 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aFull[a]);
+      a += p.splitGroups; if (a >= DWT_SLOTS) { a -= DWT_SLOTS; aph ^= 1u; }
+      j += p.splitGroups;
+      while (j >= nt) { j -= nt; step++; if (++s == p.stages) { s = 0; sph ^= 1u; } }
     }
     if (g == 0) {
     // ---- epilogue: D_j[i_local][o] -> ws[split][o*inDim + i]  (lane = i_local: coalesced along i)
@@ -433,7 +451,7 @@ size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim) {
 }
 
 int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
-                 float* dW, float* workspace, size_t wsBytes, cudaStream_t st) {
+                 float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st) {
   DwPlan q;
   if (tc_dw_plan(rows, inDim, outDim, &q) != ROC_OK) return ROC_ERR_UNSUPPORTED;
   if ((ldX % 4) || (ldDY % 4) || !aligned16(X) || !aligned16(dY)) return ROC_ERR_UNSUPPORTED;
@@ -450,6 +468,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     t.vPerSplit = ((rows + q.splits - 1) / q.splits + DWT_KS - 1) / DWT_KS * DWT_KS;
     t.tmemCols = 512; t.aCol0 = 320;
     { const char* e = getenv("ROC_TS_SPLIT"); t.splitGroups = (e && e[0] == '1') ? 1 : 2; }
+    if (dm) { t.mask = dm->bits; t.ldm = dm->ld; t.mscale = dm->scale; }
     const size_t smemTs = (size_t)q.stages * q.stageBytes + 1024 + 256;
     static size_t configuredTs = 0;
     if (smemTs > configuredTs) {
@@ -465,6 +484,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     ROC_LAUNCH_CHECK();
     return ROC_OK;
   }
+  if (dm) return ROC_ERR_UNSUPPORTED;   // only the TS kernel fuses the dropout mask
   if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
   if (!make_tmap_f32_2d(&mapDY, dY, (uint64_t)rows, (uint64_t)outDim, (uint64_t)ldDY, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
   TcDwParams p{};

@@ -14,6 +14,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp (elect.sync).  The MMA / TMA issuing loops run warp-converged and
+// branch on this only around the issue itself: under `if (lane == 0) { loop }` ptxas cannot prove
+// the tcgen05 operands warp-uniform and wraps every UTCHMMA in an ELECT / BRA.U.ANY serialisation
+// loop (~60 cycles per MMA, r1 run 21: the issuing thread, not the tensor pipe, paced the GEMM).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value ptxas knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---------------------------------------------------------------- mbarrier ---
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

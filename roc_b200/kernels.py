@@ -148,6 +148,14 @@ def dropout_fwd(x, first_row, rate, seed, step, out=None):
     return out
 
 
+def dropout_mask(rows, h, first_row, rate, seed, step, device="cuda"):
+    """Packed keep-mask [rows][round_up(ceil(h/32), 4)] uint32 (as int32 storage) of roc_dropout_fwd's mask."""
+    ldm = ((h + 31) // 32 + 3) // 4 * 4
+    m = torch.empty((rows, ldm), dtype=torch.int32, device=device)
+    check(lib.roc_dropout_mask(rows, h, first_row, rate, seed, step, _ptr(m), ldm, _stream()), "roc_dropout_mask")
+    return m
+
+
 def softmax_xent_bwd(logits, labels, mask, compact=False):
     """labels: one-hot fp32 [N][C] (reference format) or, with compact=True, int32 class ids [N]."""
     g = torch.empty_like(logits)
@@ -173,6 +181,31 @@ def linear_fwd(x, w, activation=0, norm_row_end=None, col_left=0, out=None):
     check(lib.roc_linear_fwd(x.shape[0], x.shape[1], w.shape[0], _ptr(x), _ld(x), _ptr(w), _ptr(out), _ld(out),
                              activation, flags, _ptr(norm_row_end), col_left, _stream()), "roc_linear_fwd")
     return out
+
+
+def linear_fwd_dropout(x, w, mask, rate, activation=0, norm_row_end=None, col_left=0, out=None):
+    """linear_fwd(dropout(x)) with the dropout applied while loading x (mask from dropout_mask)."""
+    assert w.is_contiguous()
+    if out is None:
+        out = padded(x.shape[0], w.shape[0], x.device)
+    flags = _lib.LINEAR_NORM_EPILOGUE if norm_row_end is not None else 0
+    check(lib.roc_linear_fwd_dropout(x.shape[0], x.shape[1], w.shape[0], _ptr(x), _ld(x), _ptr(w), _ptr(out),
+                                     _ld(out), activation, flags, _ptr(norm_row_end), col_left, _ptr(mask),
+                                     mask.stride(0) if mask is not None else 0, rate, _stream()),
+          "roc_linear_fwd_dropout")
+    return out
+
+
+def linear_bwd_dropout(x, w, y, dy, dw, mask, rate, dx=None, activation=0, accumulate_dx=False):
+    """linear_bwd where the forward input was dropout(x); dx is the gradient of x (pre-dropout)."""
+    ws_bytes = lib.roc_linear_bwd_workspace_bytes(x.shape[0], x.shape[1], w.shape[0])
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    check(lib.roc_linear_bwd_dropout(x.shape[0], x.shape[1], w.shape[0], _ptr(x), _ld(x), _ptr(w), _ptr(y),
+                                     _ld(y) if y is not None else 0, _ptr(dy), _ld(dy), _ptr(dw), _ptr(dx),
+                                     _ld(dx) if dx is not None else 0, activation, int(accumulate_dx), _ptr(ws),
+                                     ws_bytes, _ptr(mask), mask.stride(0) if mask is not None else 0, rate,
+                                     _stream()), "roc_linear_bwd_dropout")
+    return dw, dx
 
 
 def linear_bwd(x, w, y, dy, dw, dx=None, activation=0, accumulate_dx=False):

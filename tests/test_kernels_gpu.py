@@ -267,6 +267,45 @@ def test_dropout_mask_bit_exact(h, rate):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("h,rate", [(602, 0.5), (64, 0.5), (41, 0.1), (33, 0.9), (128, 0.5)])
+def test_dropout_packed_mask_bit_exact(h, rate):
+    rows, first = 300, 12345
+    keep = oracle.dropout_mask(first * h, rows * h, rate, (7 << 32) | 1, 4).reshape(rows, h)
+    m = K.dropout_mask(rows, h, first, rate, (7 << 32) | 1, 4, DEV).cpu().numpy().view(np.uint32)
+    assert m.shape[1] % 4 == 0 and m.shape[1] * 32 >= h
+    bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, -1)
+    assert np.array_equal(bits[:, :h].astype(bool), keep.astype(bool))
+    assert not bits[:, h:].any()          # pad bits / words are zero
+
+
+@pytest.mark.parametrize("n,i,o", [(1000, 602, 64), (777, 64, 41), (4099, 200, 16), (129, 16, 16), (5, 3, 2)])
+@pytest.mark.parametrize("rate", [0.5, 0.0])
+def test_linear_with_fused_dropout_matches_unfused_bitwise(n, i, o, rate):
+    """dropout applied inside the GEMM operand load == dropout kernel followed by the plain GEMM."""
+    r = np.random.RandomState(n + i)
+    first, seed, step = 77, (3 << 32) | 2, 6
+    x = K.padded(n, i, DEV, fill=torch.from_numpy(r.randn(n, i).astype(np.float32)).to(DEV))
+    w = torch.from_numpy((r.randn(o, i) * 0.1).astype(np.float32)).to(DEV)
+    dy = torch.from_numpy(r.randn(n, o).astype(np.float32)).to(DEV)
+    mask = K.dropout_mask(n, i, first, rate, seed, step, DEV) if rate > 0 else None
+    for act in (0, 1):
+        # unfused
+        xd = K.dropout_fwd(x, first, rate, seed, step)
+        y0 = K.linear_fwd(xd, w, activation=act)
+        g0 = K.padded(n, o, DEV, fill=dy)
+        dw0, dxd = torch.zeros_like(w), K.padded(n, i, DEV)
+        K.linear_bwd(xd, w, y0, g0, dw0, dxd, activation=act)
+        dx0 = K.dropout_fwd(dxd, first, rate, seed, step)      # dropout backward is the same map
+        # fused
+        y1 = K.linear_fwd_dropout(x, w, mask, rate, activation=act)
+        g1 = K.padded(n, o, DEV, fill=dy)
+        dw1, dx1 = torch.zeros_like(w), K.padded(n, i, DEV)
+        K.linear_bwd_dropout(x, w, y1, g1, dw1, mask, rate, dx=dx1, activation=act)
+        assert torch.equal(y0, y1), "fwd"
+        assert torch.equal(dw0, dw1), "dW"
+        assert torch.equal(dx0, dx1), "dX"
+
+
 def test_softmax_xent_both_label_forms():
     r = np.random.RandomState(4)
     for n, c in ((500, 7), (1000, 41), (64, 47), (10, 1)):
