@@ -19,6 +19,8 @@ int relu_bwd_inplace(int64_t rows, int H, const float* Y, int64_t ldY, float* dY
 int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
                   int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
                   cudaStream_t st);
+int tc_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
+                 int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st);
 size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim);
 int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
                  float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st);
@@ -107,7 +109,10 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
     rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
   if (rc != ROC_OK) return rc;
   if (dX) {
-    rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
+    rc = ROC_ERR_UNSUPPORTED;
+    if (!force_simt()) rc = tc_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
+    if (rc == ROC_ERR_UNSUPPORTED)
+      rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
     if (rc != ROC_OK) return rc;
   }
   return ROC_OK;

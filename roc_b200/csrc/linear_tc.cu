@@ -1,22 +1,29 @@
 // linear_tc.cu — tcgen05 / TMEM tensor-core GEMMs for the Linear op, fed by TMA.
 //
-// Replaces cublasSgemm of Linear::forward_task (linear_kernel.cu:76-80):
-//     Y[v][o] = sum_i X[v][i] * W[o*in + i]        M = rows, N = outDim, K = inDim
+// Replaces cublasSgemm of Linear::forward_task (linear_kernel.cu:76-80) and the dX sgemm of
+// Linear::backward_task (linear_kernel.cu:227-231):
+//     fwd: Y[v][o]  = sum_i X[v][i]  * W[o*in + i]      M = rows, N = outDim, K = inDim
+//     dX : dX[v][i] = sum_o dY[v][o] * W[o*in + i]      M = rows, N = inDim,  K = outDim
 // fp32 in, fp32 out, within 1e-4 of sgemm: the tensor cores have no fp32 MMA, so
 // each operand is split hi + lo (hi = fp32 truncated to TF32's 10-bit mantissa,
 // lo = exact remainder) and three kind::tf32 MMAs accumulate hi*hi + lo*hi + hi*lo
 // in fp32 TMEM (3xTF32: error ~2^-20 relative per product).
 //
-// One persistent CTA per SM, 8 warps:
-//   warp 0   TMA producer: X tile [128 rows][32 k] + W_hi / W_lo tiles, 128B swizzle,
-//            4-stage mbarrier ring
-//   warp 1   MMA issuer (one elected thread): 12 x tcgen05.mma (M128 x N x K8) per stage,
-//            tcgen05.commit frees the stage / signals the epilogue
-//   warp 2   TMEM allocator
-//   warps 4-7 operand split (X tile -> hi in place, lo beside it; fence.proxy.async)
-//            then, per tile, the epilogue: tcgen05.ld -> relu / row-norm -> global
-// The kernel is HBM-bound on X (rows*inDim*4 bytes read once); W (tens of KB) stays
-// in L2.  Roofline: DESIGN.md.
+// One kernel serves both: a row-major [rows][K] streaming operand A (X or dY) times a
+// small K-major weight operand prepared by k_split_w ([N][K] hi / lo; dX passes W
+// transposed).  The streaming operand reaches the tensor core through TMEM: moving it
+// through shared memory as hi + lo costs ~136 KB of smem traffic per k-block (~1100 smem
+// cycles against ~700 cycles of HBM time); here the split warps read the TMA tile once
+// and tcgen05.st hi / lo straight into TMEM (A operand, K-major: lane = row, column = k).
+// One persistent CTA per SM (x N-tiles of <= 128 columns in grid.y), 12 or 16 warps:
+//   warp 0     TMA producer (A tile [128 rows][32 k] + W_hi + W_lo tile per stage), elect.sync
+//   warp 1     MMA issuer: 12 x tcgen05.mma [D], [A_tmem], B_smem per stage, elect.sync
+//   warp 2     TMEM allocator (512 columns: 2 accumulators + `stages` A slots of 64)
+//   warps 4-11 split (1 or 2 groups of 4 alternate k-blocks): smem (128B-swizzled) -> regs
+//              [-> dropout mask] -> hi/lo -> tcgen05.st
+//   last 4     epilogue of tile i (relu / dropout-backward mask / relu mask / row norm /
+//              accumulate) overlaps the main loop of tile i+1 (two accumulators)
+// HBM-bound on A (rows*K*4 bytes read once); W (tens of KB) stays in L2.  Roofline: DESIGN.md.
 #include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
@@ -29,233 +36,94 @@ using namespace tc;
 constexpr int TC_BM = 128;       // rows per tile (UMMA M)
 constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
 constexpr int TC_UK = 8;         // UMMA K for tf32
-constexpr int TC_THREADS = 256;
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TS_THREADS = 512;  // launched with 384 when splitGroups == 1
+constexpr int TS_MAX_STAGES = 6;
 
-struct TcFwdParams {
-  float* Y; int64_t ldY;
-  int64_t rows; int outDim; int BN; int numKb; int stages; uint32_t tmemCols;
-  int relu;
-  const uint64_t* rowEnd; uint64_t colLeft;
-};
-
-__global__ void k_split_w(int outDim, int inDim, int BN, int Kpad, const float* __restrict__ W,
+// Whi/Wlo[n][k] (n < Npad, k < Kpad, zero padded) = split of B(n, k), where
+//   transposed == 0: B(n, k) = W[n * ldW + k]   (fwd: n = output o, k = input i, ldW = inDim)
+//   transposed == 1: B(n, k) = W[k * ldW + n]   (dX : n = input i,  k = output o)
+__global__ void k_split_w(int N, int K, int Npad, int Kpad, int ldW, int transposed, const float* __restrict__ W,
                           float* __restrict__ Whi, float* __restrict__ Wlo) {
-  int total = BN * Kpad;
+  int total = Npad * Kpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int o = i / Kpad, k = i - o * Kpad;
-    float w = (o < outDim && k < inDim) ? W[(size_t)o * inDim + k] : 0.f;
+    int n = i / Kpad, k = i - n * Kpad;
+    float w = 0.f;
+    if (n < N && k < K) w = transposed ? W[(size_t)k * ldW + n] : W[(size_t)n * ldW + k];
     float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     Whi[i] = hi;
     Wlo[i] = w - hi;
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_linear_fwd(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
-                const __grid_constant__ CUtensorMap mapWlo, const TcFwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t aBytes = TC_BM * TC_BK * 4;                 // 16 KB
-  const uint32_t bBytes = (uint32_t)p.BN * TC_BK * 4;
-  const uint32_t stageBytes = 2 * aBytes + 2 * bBytes;
-  uint8_t* barBase = smem + (size_t)p.stages * stageBytes;
-  uint64_t* fullTma = reinterpret_cast<uint64_t*>(barBase);            // [stages] TMA landed
-  uint64_t* fullSplit = fullTma + TC_MAX_STAGES;                       // [stages] hi/lo written
-  uint64_t* empty = fullSplit + TC_MAX_STAGES;                         // [stages] MMAs done with the stage
-  uint64_t* tmemFull = empty + TC_MAX_STAGES;                          // accumulator complete
-  uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(tmemFull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t numTiles = (p.rows + TC_BM - 1) / TC_BM;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWhi); tma_prefetch_desc(&mapWlo);
-    for (int s = 0; s < p.stages; s++) { mbar_init(&fullTma[s], 1); mbar_init(&fullSplit[s], 4); mbar_init(&empty[s], 1); }
-    mbar_init(tmemFull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmemAddr, p.tmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmemBase = *tmemAddr;
-
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.numKb; kb++) {
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = smem + (size_t)s * stageBytes;
-          mbar_arrive_expect_tx(&fullTma[s], aBytes + 2 * bBytes);
-          tma_load_2d(st, &mapX, kb * TC_BK, (int)(tile * TC_BM), &fullTma[s]);
-          tma_load_2d(st + 2 * aBytes, &mapWhi, kb * TC_BK, 0, &fullTma[s]);
-          tma_load_2d(st + 2 * aBytes + bBytes, &mapWlo, kb * TC_BK, 0, &fullTma[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================= MMA issuer =================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN, 0, 0);
-      int s = 0; uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.numKb; kb++) {
-          mbar_wait(&fullSplit[s], ph);
-          tc_fence_after();
-          const uint32_t aHi = smem_u32(smem + (size_t)s * stageBytes);
-          const uint32_t aLo = aHi + aBytes;
-          const uint32_t bHi = aHi + 2 * aBytes;
-          const uint32_t bLo = bHi + bBytes;
-#pragma unroll
-          for (int k = 0; k < TC_BK / TC_UK; k++) {
-            const uint32_t off = k * TC_UK * 4;   // bytes along K inside the swizzled row
-            const uint64_t dAh = make_sdesc_sw128(aHi + off, 16, 1024), dAl = make_sdesc_sw128(aLo + off, 16, 1024);
-            const uint64_t dBh = make_sdesc_sw128(bHi + off, 16, 1024), dBl = make_sdesc_sw128(bLo + off, 16, 1024);
-            umma_tf32(tmemBase, dAl, dBh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(tmemBase, dAh, dBl, idesc, 1u);
-            umma_tf32(tmemBase, dAh, dBh, idesc, 1u);
-          }
-          umma_commit(&empty[s]);                          // stage reusable once these MMAs retire
-          if (kb == p.numKb - 1) umma_commit(tmemFull);   // accumulator of this tile complete
-          if (++s == p.stages) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== operand split, then the tile epilogue ==================
-    const int t = threadIdx.x - 128;    // 0..127
-    int s = 0; uint32_t ph = 0; uint32_t tilePh = 0;
-    for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-      for (int kb = 0; kb < p.numKb; kb++) {
-        mbar_wait(&fullTma[s], ph);
-        float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stageBytes);
-        float4* al = reinterpret_cast<float4*>(smem + (size_t)s * stageBytes + aBytes);
-#pragma unroll
-        for (int j = 0; j < (TC_BM * TC_BK / 4) / 128; j++) {
-          const int i = j * 128 + t;
-          float4 v = a[i], h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          a[i] = h; al[i] = l;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&fullSplit[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-      }
-      // ---- epilogue: TMEM lane = row of the tile; this warp owns lanes 32*(warp%4)..+31
-      mbar_wait(tmemFull, tilePh);
-      tilePh ^= 1;
-      tc_fence_after();
-      const int64_t row = tile * TC_BM + (warp - 4) * 32 + lane;
-      float d = 1.0f;
-      if (p.rowEnd && row < p.rows) {
-        uint64_t st = (row == 0) ? p.colLeft : p.rowEnd[row - 1];
-        d = sqrtf((float)(uint32_t)(p.rowEnd[row] - st));
-      }
-      const RowDiv rd = rowdiv_make(d);
-      const uint32_t taddr = tmemBase + ((uint32_t)((warp - 4) * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (row < p.rows) {
-          float* y = p.Y + row * p.ldY + c0;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              float x = __uint_as_float(r[q * 4 + k]);
-              if (p.relu) x = relu_nanprop(x);
-              if (p.rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
-              v[k] = x;
-            }
-            const int c = c0 + q * 4;
-            if (c + 4 <= p.outDim) *reinterpret_cast<float4*>(y + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
-            else
-#pragma unroll
-              for (int k = 0; k < 4; k++) if (c + k < p.outDim) y[q * 4 + k] = v[k];
-          }
-        }
-      }
-      tc_fence_before();   // TMEM reads done before the next tile's first MMA may overwrite it
-    }
-  }
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
-}
-
-// ---------------------------------------------------------------------------
-// TS variant: the X operand reaches the tensor core through TMEM instead of smem.
-// The SS kernel above moves every X element through shared memory five times (TMA
-// write, split read, hi+lo write, 3 MMA operand reads ~ 136 KB per k-block, ~1100
-// smem cycles against ~700 cycles of HBM time for the same k-block); here the
-// split warps read the TMA tile once and tcgen05.st hi / lo straight into TMEM
-// (A operand, K-major: lane = row, column = k), so smem carries 16 KB in + 16 KB
-// out of X and the W tiles only.  12 warps:
-//   warp 0    TMA producer (X tile + W_hi + W_lo per stage)
-//   warp 1    MMA issuer: 12 x tcgen05.mma [D], [A_tmem], B_smem per stage
-//   warp 2    TMEM allocator (512 columns: 2 accumulators + `stages` A slots of 64)
-//   warps 4-7 split: smem (128B-swizzled) -> regs -> hi/lo -> tcgen05.st
-//   warps 8-11 epilogue of tile i overlaps the main loop of tile i+1 (two accumulators)
-constexpr int TS_THREADS = 512;      // launched with 384 when splitGroups == 1
-constexpr int TS_MAX_STAGES = 6;
-
 struct TcTsParams {
   float* Y; int64_t ldY;
   int64_t rows; int outDim; int BN; int numKb; int stages;
   uint32_t tmemCols, dStride, aCol0;
   int splitGroups;      // 1 or 2 warpgroups of split warps (alternate k-blocks)
-  const uint32_t* mask; int64_t ldm; float mscale;   // fused dropout of X (NULL = none)
-  int relu;
-  const uint64_t* rowEnd; uint64_t colLeft;
+  const uint32_t* mask; int64_t ldm; float mscale;      // dropout of A fused into the operand load (NULL = none)
+  // epilogue, applied in this order to acc(row, col):
+  int relu;                                             //   relu (Linear's activation, linear_kernel.cu:83-104)
+  const uint32_t* omask; int64_t oldm; float oscale;    //   dropout backward: keep ? x * scale : 0
+  const float* reluOf; int64_t ldR;                     //   relu backward: reluOf(row, col) > 0 ? x : 0
+  const uint64_t* rowEnd; uint64_t colLeft;             //   indegree norm: x / sqrtf(deg(row))
+  int accumulate;                                       //   Y += x instead of Y = x
 };
 
-__device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int BN, int outDim, int64_t row, int64_t rows,
-                                                 float* Y, int64_t ldY, int relu, const uint64_t* rowEnd,
-                                                 uint64_t colLeft) {
+__device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t row, const TcTsParams& p) {
   float d = 1.0f;
-  if (rowEnd && row < rows) {
-    uint64_t st = (row == 0) ? colLeft : rowEnd[row - 1];
-    d = sqrtf((float)(uint32_t)(rowEnd[row] - st));
+  if (p.rowEnd && row < p.rows) {
+    uint64_t st = (row == 0) ? p.colLeft : p.rowEnd[row - 1];
+    d = sqrtf((float)(uint32_t)(p.rowEnd[row] - st));
   }
   const RowDiv rd = rowdiv_make(d);
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  for (int c0 = 0; c0 < p.BN; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(taddr + (uint32_t)c0, r);
     tmem_ld_wait();
-    if (row < rows) {
-      float* y = Y + row * ldY + c0;
+    const int col0 = n0 + c0;
+    if (row < p.rows && col0 < p.outDim) {
+      float* y = p.Y + row * p.ldY + col0;
+      uint32_t mw = 0xFFFFFFFFu;      // the 16 columns of this chunk lie in one mask word (col0 % 16 == 0)
+      if (p.omask) mw = __ldg(p.omask + row * p.oldm + (col0 >> 5)) >> (col0 & 31);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        float v[4];
+        const int c = col0 + q * 4;
+        const bool full = c + 4 <= p.outDim;
+        float v[4], old[4] = {0.f, 0.f, 0.f, 0.f}, ro[4] = {1.f, 1.f, 1.f, 1.f};
+        if (p.accumulate) {
+          if (full) *reinterpret_cast<float4*>(old) = *reinterpret_cast<const float4*>(y + q * 4);
+          else
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (c + k < p.outDim) old[k] = y[q * 4 + k];
+        }
+        if (p.reluOf) {
+          const float* rp = p.reluOf + row * p.ldR + c;
+          if (full) *reinterpret_cast<float4*>(ro) = __ldg(reinterpret_cast<const float4*>(rp));
+          else
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (c + k < p.outDim) ro[k] = rp[k];
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           float x = __uint_as_float(r[q * 4 + k]);
-          if (relu) x = relu_nanprop(x);
-          if (rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
+          if (p.relu) x = relu_nanprop(x);
+          if (p.omask) x = ((mw >> (q * 4 + k)) & 1u) ? x * p.oscale : 0.f;
+          if (p.reluOf) x = (ro[k] > 0.f) ? x : 0.f;
+          if (p.rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
+          if (p.accumulate) x = old[k] + x;
           v[k] = x;
         }
-        const int c = c0 + q * 4;
-        if (c + 4 <= outDim) *reinterpret_cast<float4*>(y + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        if (full) *reinterpret_cast<float4*>(y + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
         else
 #pragma unroll
-          for (int k = 0; k < 4; k++) if (c + k < outDim) y[q * 4 + k] = v[k];
+          for (int k = 0; k < 4; k++) if (c + k < p.outDim) y[q * 4 + k] = v[k];
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
-k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
+k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
                    const __grid_constant__ CUtensorMap mapWlo, const TcTsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -272,6 +140,7 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t numTiles = (p.rows + TC_BM - 1) / TC_BM;
+  const int n0 = blockIdx.y * p.BN;          // this CTA's slice of the N (output column) dimension
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWhi); tma_prefetch_desc(&mapWlo);
@@ -295,8 +164,8 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], aBytes + 2 * bBytes);
           tma_load_2d(st, &mapX, kb * TC_BK, (int)(tile * TC_BM), &full[s]);
-          tma_load_2d(st + aBytes, &mapWhi, kb * TC_BK, 0, &full[s]);
-          tma_load_2d(st + aBytes + bBytes, &mapWlo, kb * TC_BK, 0, &full[s]);
+          tma_load_2d(st + aBytes, &mapWhi, kb * TC_BK, n0, &full[s]);
+          tma_load_2d(st + aBytes + bBytes, &mapWlo, kb * TC_BK, n0, &full[s]);
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -394,7 +263,7 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
       tc_fence_after();
       const int64_t row = tile * TC_BM + (warp & 3) * 32 + lane;
       const uint32_t taddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16) + b * p.dStride;
-      tc_epilogue_rows(taddr, p.BN, p.outDim, row, p.rows, p.Y, p.ldY, p.relu, p.rowEnd, p.colLeft);
+      tc_epilogue_rows(taddr, n0, row, p);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dEmpty[b]);
@@ -408,82 +277,91 @@ k_tc_linear_fwd_ts(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 static float* g_wsplit = nullptr;
 static size_t g_wsplitFloats = 0;
 
-int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
-                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
-                  cudaStream_t st) {
-  if (outDim > 256 || inDim < 8 || rows < 1) return ROC_ERR_UNSUPPORTED;
-  if ((ldX % 4) || (ldY % 4) || !aligned16(X) || !aligned16(Y)) return ROC_ERR_UNSUPPORTED;
+struct TsEpilogue {
+  int relu = 0;
+  const DropMask* outMask = nullptr;
+  const float* reluOf = nullptr; int64_t ldR = 0;
+  const uint64_t* rowEnd = nullptr; uint64_t colLeft = 0;
+  int accumulate = 0;
+};
+
+// Y[rows][N] (op)= A[rows][K] * B^T with B(n, k) taken from W as k_split_w describes
+static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, const float* W, int ldW, int transposed,
+                   float* Y, int64_t ldY, const DropMask* inMask, const TsEpilogue& e, cudaStream_t st) {
+  if (K < 8 || N < 1 || rows < 1) return ROC_ERR_UNSUPPORTED;
+  if ((ldA % 4) || (ldY % 4) || !aligned16(A) || !aligned16(Y)) return ROC_ERR_UNSUPPORTED;
+  if (e.reluOf && ((e.ldR % 4) || !aligned16(e.reluOf))) return ROC_ERR_UNSUPPORTED;
   if (rows > 0x7FFFFF00ll) return ROC_ERR_UNSUPPORTED;   // TMA coordinates are int32
   if (!encode_tiled_fn()) return ROC_ERR_UNSUPPORTED;
-  const int BN = (outDim + 15) / 16 * 16;
-  const int Kpad = (inDim + TC_BK - 1) / TC_BK * TC_BK;
-  const size_t need = (size_t)2 * BN * Kpad;
+  { const char* g = getenv("ROC_B200_GEMM"); if (g && g[0] == 'n' && g[1] == 'o') return ROC_ERR_UNSUPPORTED; }   // "notc"
+  int BN = (N + 15) / 16 * 16;
+  if (BN > 128) BN = 128;
+  const int nTiles = (N + BN - 1) / BN;
+  const int Npad = nTiles * BN;
+  const int Kpad = (K + TC_BK - 1) / TC_BK * TC_BK;
+  const size_t need = (size_t)2 * Npad * Kpad;
   if (need > g_wsplitFloats) {
     if (g_wsplit) { ROC_CUDA(cudaDeviceSynchronize()); ROC_CUDA(cudaFree(g_wsplit)); g_wsplit = nullptr; g_wsplitFloats = 0; }
     ROC_CUDA(cudaMalloc(&g_wsplit, need * sizeof(float)));
     g_wsplitFloats = need;
   }
   float* Whi = g_wsplit;
-  float* Wlo = g_wsplit + (size_t)BN * Kpad;
-  k_split_w<<<(BN * Kpad + 255) / 256, 256, 0, st>>>(outDim, inDim, BN, Kpad, W, Whi, Wlo);
+  float* Wlo = g_wsplit + (size_t)Npad * Kpad;
+  k_split_w<<<(Npad * Kpad + 255) / 256, 256, 0, st>>>(N, K, Npad, Kpad, ldW, transposed, W, Whi, Wlo);
   ROC_LAUNCH_CHECK();
 
-  CUtensorMap mapX, mapWhi, mapWlo;
-  if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, TC_BM, TC_BK)) return ROC_ERR_UNSUPPORTED;
-  if (!make_tmap_f32_2d(&mapWhi, Whi, (uint64_t)BN, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
-  if (!make_tmap_f32_2d(&mapWlo, Wlo, (uint64_t)BN, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
+  CUtensorMap mapA, mapWhi, mapWlo;
+  if (!make_tmap_f32_2d(&mapA, A, (uint64_t)rows, (uint64_t)K, (uint64_t)ldA, TC_BM, TC_BK)) return ROC_ERR_UNSUPPORTED;
+  if (!make_tmap_f32_2d(&mapWhi, Whi, (uint64_t)Npad, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
+  if (!make_tmap_f32_2d(&mapWlo, Wlo, (uint64_t)Npad, (uint64_t)Kpad, (uint64_t)Kpad, (uint32_t)BN, TC_BK)) return ROC_ERR_UNSUPPORTED;
 
-  const int64_t numTiles = (rows + TC_BM - 1) / TC_BM;
-  int grid = sm_count();
-  if (numTiles < grid) grid = (int)numTiles;
-  {
-    // TS path: 2 accumulators of dStride columns + `stages` A slots of 64 columns in 512 TMEM columns
-    const char* g = getenv("ROC_B200_GEMM");
-    const uint32_t dStride = (uint32_t)((BN + 31) / 32 * 32);
-    const size_t stageBytesTs = (size_t)TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
-    int stagesTs = (int)((512 - 2 * dStride) / 64);
-    if (stagesTs > TS_MAX_STAGES) stagesTs = TS_MAX_STAGES;
-    while (stagesTs > 0 && (size_t)stagesTs * stageBytesTs + 1024 + 256 > (size_t)220 * 1024) stagesTs--;
-    if (stagesTs >= 3 && !(g && g[0] == 's' && g[1] == 's')) {
-      TcTsParams q{};
-      q.Y = Y; q.ldY = ldY; q.rows = rows; q.outDim = outDim; q.BN = BN; q.numKb = Kpad / TC_BK;
-      q.stages = stagesTs; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
-      q.relu = relu; q.rowEnd = rowEnd; q.colLeft = colLeft;
-      { const char* e = getenv("ROC_TS_SPLIT"); q.splitGroups = (e && e[0] == '1') ? 1 : 2; }
-      if (dm) { q.mask = dm->bits; q.ldm = dm->ld; q.mscale = dm->scale; }
-      const size_t smemTs = (size_t)stagesTs * stageBytesTs + 1024 + 256;
-      static size_t configuredTs = 0;
-      if (smemTs > configuredTs) {
-        ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemTs));
-        configuredTs = smemTs;
-      }
-      k_tc_linear_fwd_ts<<<grid, 256 + 128 * q.splitGroups, smemTs, st>>>(mapX, mapWhi, mapWlo, q);
-      ROC_LAUNCH_CHECK();
-      return ROC_OK;
-    }
-  }
-
-  if (dm) return ROC_ERR_UNSUPPORTED;   // only the TS kernel fuses the dropout mask
-  TcFwdParams p{};
-  p.Y = Y; p.ldY = ldY; p.rows = rows; p.outDim = outDim; p.BN = BN; p.numKb = Kpad / TC_BK;
-  p.relu = relu; p.rowEnd = rowEnd; p.colLeft = colLeft;
-  uint32_t cols = 32;
-  while ((int)cols < BN) cols <<= 1;
-  p.tmemCols = cols;
-  const size_t stageBytes = (size_t)2 * TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
-  int stages = (int)((200 * 1024) / stageBytes);
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (stages < 2) return ROC_ERR_UNSUPPORTED;
-  p.stages = stages;
-  const size_t smemBytes = (size_t)stages * stageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // 2 accumulators of dStride columns + `stages` A slots of 64 columns in the 512 TMEM columns
+  const uint32_t dStride = (uint32_t)((BN + 31) / 32 * 32);
+  const size_t stageBytes = (size_t)TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
+  int stages = (int)((512 - 2 * dStride) / 64);
+  if (stages > TS_MAX_STAGES) stages = TS_MAX_STAGES;
+  while (stages > 0 && (size_t)stages * stageBytes + 1024 + 256 > (size_t)220 * 1024) stages--;
+  if (stages < 3) return ROC_ERR_UNSUPPORTED;
+  TcTsParams q{};
+  q.Y = Y; q.ldY = ldY; q.rows = rows; q.outDim = N; q.BN = BN; q.numKb = Kpad / TC_BK;
+  q.stages = stages; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
+  { const char* s2 = getenv("ROC_TS_SPLIT"); q.splitGroups = (s2 && s2[0] == '1') ? 1 : 2; }
+  if (inMask) { q.mask = inMask->bits; q.ldm = inMask->ld; q.mscale = inMask->scale; }
+  q.relu = e.relu;
+  if (e.outMask) { q.omask = e.outMask->bits; q.oldm = e.outMask->ld; q.oscale = e.outMask->scale; }
+  q.reluOf = e.reluOf; q.ldR = e.ldR;
+  q.rowEnd = e.rowEnd; q.colLeft = e.colLeft;
+  q.accumulate = e.accumulate;
+  const size_t smemBytes = (size_t)stages * stageBytes + 1024 + 256;
   static size_t configured = 0;
   if (smemBytes > configured) {
-    ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
     configured = smemBytes;
   }
-  k_tc_linear_fwd<<<grid, TC_THREADS, smemBytes, st>>>(mapX, mapWhi, mapWlo, p);
+  const int64_t numTiles = (rows + TC_BM - 1) / TC_BM;
+  int gx = sm_count() / nTiles;
+  if (gx < 1) gx = 1;
+  if (numTiles < gx) gx = (int)numTiles;
+  dim3 grid((unsigned)gx, (unsigned)nTiles, 1);
+  k_tc_linear_ts<<<grid, 256 + 128 * q.splitGroups, smemBytes, st>>>(mapA, mapWhi, mapWlo, q);
   ROC_LAUNCH_CHECK();
   return ROC_OK;
+}
+
+int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W, float* Y,
+                  int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
+                  cudaStream_t st) {
+  TsEpilogue e;
+  e.relu = relu; e.rowEnd = rowEnd; e.colLeft = colLeft;
+  return ts_gemm(rows, inDim, outDim, X, ldX, W, inDim, 0, Y, ldY, dm, e, st);
+}
+
+// dX (+)= dY W, optionally followed in the epilogue by the dropout backward of X's producer
+int tc_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
+                 int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st) {
+  TsEpilogue e;
+  e.outMask = dm; e.accumulate = accumulate;
+  return ts_gemm(rows, outDim, inDim, dY, ldDY, W, inDim, 1, dX, ldDX, nullptr, e, st);
 }
 
 }  // namespace roc

@@ -199,7 +199,7 @@ struct TcDwTsParams {
 
 __global__ void __launch_bounds__(384, 1)
 k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
-                  const TcDwTsParams p) {
+                  const __grid_constant__ CUtensorMap mapM, const TcDwTsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int g0 = blockIdx.y * p.G;
@@ -207,7 +207,9 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const uint32_t xTile = DWT_KS * DW_BM * 4;                         // 8 KB per M-tile
   const uint32_t xBytes = (uint32_t)p.G * xTile;
   const uint32_t bBytes = (uint32_t)p.nbAtoms * 1024u * (DWT_KS / 8);  // raw dY (later hi), lo beside it
-  const uint32_t stageBytes = xBytes + 2 * bBytes;
+  const uint32_t mBox = (uint32_t)DWT_KS * (uint32_t)p.G * 4u * 4u;   // mask box: KS rows x (4 words per M-tile)
+  const uint32_t mBytes = p.mask ? (mBox + 1023u) / 1024u * 1024u : 0u;
+  const uint32_t stageBytes = xBytes + 2 * bBytes + mBytes;
   uint8_t* barBase = smem + (size_t)p.stages * stageBytes;
   uint64_t* fullTma = reinterpret_cast<uint64_t*>(barBase);          // [stages]
   uint64_t* bFull = fullTma + DWT_MAX_STAGES;                        // [stages] dY hi/lo ready in smem
@@ -224,6 +226,7 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapDY);
+    if (p.mask) tma_prefetch_desc(&mapM);
     for (int s = 0; s < p.stages; s++) { mbar_init(&fullTma[s], 1); mbar_init(&bFull[s], 4); mbar_init(&empty[s], 1); }
     for (int a = 0; a < DWT_SLOTS; a++) { mbar_init(&aFull[a], 4); mbar_init(&aEmpty[a], 1); }
     mbar_init(tmemFull, 1);
@@ -238,7 +241,7 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer ================================
     int s = 0; uint32_t ph = 0;
-    const uint32_t tx = (uint32_t)nt * xTile + bBytes;
+    const uint32_t tx = (uint32_t)nt * xTile + bBytes + (p.mask ? mBox : 0u);
     for (int step = 0; step < numSteps; step++) {
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + (size_t)s * stageBytes;
@@ -249,6 +252,7 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int ks = 0; ks < DWT_KS / 8; ks++)
           for (int b = 0; b < p.nbAtoms; b++)
             tma_load_2d(st + xBytes + (size_t)(ks * p.nbAtoms + b) * 1024, &mapDY, b * 32, v + ks * 8, &fullTma[s]);
+        if (p.mask) tma_load_2d(st + xBytes + 2 * bBytes, &mapM, g0 * 4, v, &fullTma[s]);
       }
       __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -304,14 +308,6 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     int a = g % DWT_SLOTS; uint32_t aph = 0;
     for (int64_t it = g; it < iters; it += p.splitGroups) {
       uint8_t* st = smem + (size_t)s * stageBytes;
-      // dropout fused into the operand load: this warp's 32 X columns are one mask word per vertex
-      uint32_t mk[DWT_KS];
-      if (masked) {
-        const int64_t v = v0 + (int64_t)step * DWT_KS;
-        const uint32_t* mrow = p.mask + (int64_t)((g0 + j) * 4 + (warp & 3));
-#pragma unroll
-        for (int k = 0; k < DWT_KS; k++) mk[k] = __ldg(mrow + min(v + k, p.rows - 1) * p.ldm);
-      }
       if (step != lastStep) {
         lastStep = step;
         mbar_wait(&fullTma[s], sph);
@@ -332,11 +328,14 @@ k_tc_linear_dw_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
       const float* x = reinterpret_cast<const float*>(st + (size_t)j * xTile) + t;   // [KS][128]: column t
+      // dropout fused into the operand load: this warp's 32 X columns are one mask word per vertex,
+      // TMA'd beside the X tile as [KS][4 G] words
+      const uint32_t* mk = reinterpret_cast<const uint32_t*>(st + xBytes + 2 * bBytes) + j * 4 + (warp & 3);
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int k = 0; k < DWT_KS; k++) {
         float e = x[k * DW_BM];
-        if (masked) e = ((mk[k] >> lane) & 1u) ? e * p.mscale : 0.f;   // == k_dropout
+        if (masked) e = ((mk[k * p.G * 4] >> lane) & 1u) ? e * p.mscale : 0.f;   // == k_dropout
         const uint32_t h = __float_as_uint(e) & 0xFFFFE000u;
         hi[k] = h;
         lo[k] = __float_as_uint(e - __uint_as_float(h));
@@ -412,7 +411,7 @@ static int tc_dw_plan(int64_t rows, int inDim, int outDim, DwPlan* q) {
       q->ts = true;
       q->G = g;
       q->groups = (q->MT + g - 1) / g;
-      q->stageBytes = (size_t)g * DWT_KS * DW_BM * 4 + (size_t)2 * q->nb * 1024 * (DWT_KS / 8);
+      q->stageBytes = (size_t)g * DWT_KS * DW_BM * 4 + (size_t)2 * q->nb * 1024 * (DWT_KS / 8) + 2048 /* mask box */;
       int st = (int)((200 * 1024) / q->stageBytes);
       if (st > DWT_MAX_STAGES) st = DWT_MAX_STAGES;
       q->stages = st;
@@ -468,7 +467,13 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     t.vPerSplit = ((rows + q.splits - 1) / q.splits + DWT_KS - 1) / DWT_KS * DWT_KS;
     t.tmemCols = 512; t.aCol0 = 320;
     { const char* e = getenv("ROC_TS_SPLIT"); t.splitGroups = (e && e[0] == '1') ? 1 : 2; }
-    if (dm) { t.mask = dm->bits; t.ldm = dm->ld; t.mscale = dm->scale; }
+    CUtensorMap mapM = mapDY;   // placeholder when there is no mask (never dereferenced)
+    if (dm) {
+      t.mask = dm->bits; t.ldm = dm->ld; t.mscale = dm->scale;
+      if ((size_t)DWT_KS * q.G * 16 > 2048) return ROC_ERR_UNSUPPORTED;
+      if (!make_tmap_u32_2d(&mapM, dm->bits, (uint64_t)rows, (uint64_t)dm->ld, (uint64_t)dm->ld, DWT_KS, (uint32_t)q.G * 4))
+        return ROC_ERR_UNSUPPORTED;
+    }
     const size_t smemTs = (size_t)q.stages * q.stageBytes + 1024 + 256;
     static size_t configuredTs = 0;
     if (smemTs > configuredTs) {
@@ -476,7 +481,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
       configuredTs = smemTs;
     }
     dim3 gridTs((unsigned)q.splits, (unsigned)q.groups, 1);
-    k_tc_linear_dw_ts<<<gridTs, 128 + 128 * t.splitGroups, smemTs, st>>>(mapX, mapDY, t);
+    k_tc_linear_dw_ts<<<gridTs, 128 + 128 * t.splitGroups, smemTs, st>>>(mapX, mapDY, mapM, t);
     ROC_LAUNCH_CHECK();
     int64_t blocksTs = ((int64_t)count + 255) / 256;
     if (blocksTs > sm_count() * 8) blocksTs = sm_count() * 8;
