@@ -195,11 +195,13 @@ int roc_add_bwd(int64_t rows, int H, const float* dY, int64_t ldDY, float* dA,
 
 /* Replaces cudnnDropoutForward/Backward, dropout_kernel.cu:98-99, 149-150.
  * y = keep ? x / (1 - rate) : 0.  cuDNN's generator is not reproducible, so the
- * mask is defined here instead: element (globalRow, h) of a width-H tensor has
- * dense index k = globalRow*H + h and keeps iff word (k & 3) of
- * Philox4x32-10(counter = {k>>2 lo, k>>2 hi, step, 0}, key = {seed lo, seed hi})
- * >= rate * 2^32.  The mask is recomputed in bwd (no reserve space).
- * `firstRow` = global index of the slab's first row (rowLeft). */
+ * mask is defined here instead: element (globalRow r, column c) keeps iff 16-bit
+ * lane (c & 7) of Philox4x32-10(counter = {r lo, r hi, c >> 3, step},
+ * key = {seed lo, seed hi}) >= round(rate * 65536); lanes are numbered low half
+ * of word 0, high half of word 0, low half of word 1, ...  One Philox block
+ * decides 8 consecutive columns of one row; the mask does not depend on the
+ * tensor's width or on how rows are split across GPUs.  It is recomputed in bwd
+ * (no reserve space).  `firstRow` = global index of the slab's first row (rowLeft). */
 int roc_dropout_fwd(int64_t rows, int H, int64_t firstRow, float rate, uint64_t seed,
                     uint32_t step, const float* x, int64_t ldX, float* y, int64_t ldY,
                     roc_stream_t stream);

@@ -142,11 +142,18 @@ def activation_bwd(y, dy, mode, dx=None):
     return dx
 
 
-def dropout_mask(first_elem, n, rate, seed, step):
-    keep = np.empty(n, dtype=np.uint8)
-    lib().roc_oracle_dropout_mask(C.c_int64(first_elem), C.c_int64(n), C.c_float(rate), C.c_uint64(seed),
-                                  C.c_uint32(step), _p(keep))
+def dropout_mask(first_row, rows, h, rate, seed, step):
+    """keep[rows][h] (uint8) of rows first_row.. of a width-h tensor (roc_oracle_dropout_mask)."""
+    keep = np.empty((rows, h), dtype=np.uint8)
+    lib().roc_oracle_dropout_mask(C.c_int64(first_row), C.c_int64(rows), C.c_int(h), C.c_float(rate),
+                                  C.c_uint64(seed), C.c_uint32(step), _p(keep))
     return keep
+
+
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32); k = np.asarray(key, dtype=np.uint32); o = np.empty(4, dtype=np.uint32)
+    lib().roc_oracle_philox4x32_10(_p(c), _p(k), _p(o))
+    return o
 
 
 def dropout_apply(x, keep, rate):
@@ -262,7 +269,7 @@ class GcnOracle:
             rate = self.dropout if train else 0.0
             if rate > 0.0:
                 key = (self.dropout_seed << 32) | self._dropout_op_index(i)
-                keep = dropout_mask(0, t.size, rate, key, self.step).reshape(t.shape)
+                keep = dropout_mask(0, t.shape[0], t.shape[1], rate, key, self.step)
                 d = dropout_apply(t, keep, rate)
             else:
                 keep = None

@@ -342,20 +342,33 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-/* keep[k] = 1 if u32 random >= rate * 2^32.  Element k of the tensor (dense
- * [N][H] index, global row) draws word (k & 3) of Philox counter
- * (k>>2 lo, k>>2 hi, step, 0) under key (seed lo, seed hi). */
-void roc_oracle_dropout_mask(int64_t first, int64_t n, float rate,
+/* the raw generator, exposed so the tests can pin it to Random123's known-answer vectors */
+void roc_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  philox4x32_10(c, key[0], key[1]);
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+/* keep[(r - firstRow) * H + c] for rows firstRow .. firstRow+rows-1 of a width-H tensor:
+ * element (global row r, column c) keeps iff 16-bit lane (c & 7) of Philox counter
+ * (r lo, r hi, c >> 3, step) under key (seed lo, seed hi) is >= round(rate * 65536);
+ * lanes are numbered low half of word 0, high half of word 0, low half of word 1, ...
+ * (include/roc_b200.h, roc_dropout_fwd). */
+void roc_oracle_dropout_mask(int64_t firstRow, int64_t rows, int H, float rate,
                              uint64_t seed, uint32_t step, uint8_t* keep) {
-  double t = (double)rate * 4294967296.0;
-  uint32_t thresh = (t >= 4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t;
+  double t = (double)rate * 65536.0 + 0.5;
+  uint32_t thresh = (t >= 65535.0) ? 65535u : (uint32_t)t;
 #pragma omp parallel for schedule(static)
-  for (int64_t j = 0; j < n; j++) {
-    uint64_t k = (uint64_t)(first + j);
-    uint64_t q = k >> 2;
-    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), step, 0u};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    keep[j] = (c[k & 3] >= thresh) ? 1 : 0;
+  for (int64_t j = 0; j < rows; j++) {
+    uint64_t r = (uint64_t)(firstRow + j);
+    for (int g = 0; g * 8 < H; g++) {
+      uint32_t c[4] = {(uint32_t)r, (uint32_t)(r >> 32), (uint32_t)g, step};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      for (int l = 0; l < 8 && g * 8 + l < H; l++) {
+        uint32_t u16 = (c[l >> 1] >> (16 * (l & 1))) & 0xFFFFu;
+        keep[(size_t)j * H + g * 8 + l] = (u16 >= thresh) ? 1 : 0;
+      }
+    }
   }
 }
 

@@ -140,73 +140,83 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
   }
 }
 
-__host__ __device__ inline uint32_t dropout_thresh(float rate) {
-  double t = (double)rate * 4294967296.0;
-  return (t >= 4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t;
+// keep(row, col) = 16-bit lane (col & 7) of Philox4x32-10(counter = {row lo, row hi, col >> 3, step},
+// key = {seed lo, seed hi}) >= T16, lanes numbered low half of word 0, high half of word 0, low half
+// of word 1, ...  T16 = round(rate * 65536): one Philox call decides 8 consecutive columns of a row.
+__host__ __device__ inline uint32_t dropout_thresh16(float rate) {
+  double t = (double)rate * 65536.0 + 0.5;
+  return (t >= 65535.0) ? 65535u : (uint32_t)t;
+}
+// bit l of the result = keep of lane l (l = 0..7) of one Philox block
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t row, uint32_t grp, uint32_t step, uint32_t seedLo,
+                                                  uint32_t seedHi, uint32_t thresh16) {
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), grp, step};
+  philox4x32_10(c, seedLo, seedHi);
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int w = 3; w >= 0; w--) {
+    bits = bits + bits + ((c[w] >> 16) >= thresh16 ? 1u : 0u);
+    bits = bits + bits + ((c[w] & 0xFFFFu) >= thresh16 ? 1u : 0u);
+  }
+  return bits;
 }
 
-// One thread handles UNR x 4 consecutive columns of UNR different rows-chunks per iteration
-// (all loads issued before the Philox rounds: the single-float4 version ran at 3.9 TB/s,
-// latency-bound).  VEC == 1 is the scalar fallback for unpadded layouts.
+// One thread handles the 8 columns of one Philox block of UNR different (row, block) items per
+// iteration, all loads issued before the Philox rounds.  VEC == 1 is the scalar fallback for
+// unpadded layouts.
 template <int VEC, int UNR>
 __global__ void __launch_bounds__(EW_T)
-k_dropout(int64_t rows, int H, int64_t firstRow, uint32_t thresh, float scale, uint32_t seedLo,
+k_dropout(int64_t rows, int H, int64_t firstRow, uint32_t thresh16, float scale, uint32_t seedLo,
           uint32_t seedHi, uint32_t step, const float* __restrict__ x, int64_t ldx,
           float* __restrict__ y, int64_t ldy) {
-  const int Wq = (H + VEC - 1) / VEC;
+  const int Wq = (H + 7) / 8;
   const int64_t total = rows * (int64_t)Wq;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNR) {
-    float xv[UNR][VEC];
-    int64_t rr[UNR]; int cc[UNR]; bool full[UNR];
+    float xv[UNR][8];
+    int64_t rr[UNR]; int cc[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; u++) {
       const int64_t i = i0 + u * stride;
       const bool ok = i < total;
       const int64_t r = ok ? i / Wq : 0;
-      const int c = ok ? (int)(i - r * Wq) * VEC : 0;
+      const int c = ok ? (int)(i - r * Wq) * 8 : 0;
       rr[u] = ok ? r : -1; cc[u] = c;
-      full[u] = ok && (VEC == 4) && (c + 4 <= H);
-      if (full[u]) *reinterpret_cast<float4*>(xv[u]) = *reinterpret_cast<const float4*>(x + r * ldx + c);
-      else
 #pragma unroll
-        for (int j = 0; j < VEC; j++) xv[u][j] = (ok && c + j < H) ? x[r * ldx + c + j] : 0.f;
+      for (int h = 0; h < 2; h++) {
+        const int ch = c + 4 * h;
+        if (ok && VEC == 4 && ch + 4 <= H)
+          *reinterpret_cast<float4*>(&xv[u][4 * h]) = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+        else
+#pragma unroll
+          for (int j = 0; j < 4; j++) xv[u][4 * h + j] = (ok && ch + j < H) ? x[r * ldx + ch + j] : 0.f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNR; u++) {
       if (rr[u] < 0) continue;
       const int64_t r = rr[u]; const int c = cc[u];
-      const uint64_t k = (uint64_t)(firstRow + r) * (uint64_t)H + (uint64_t)c;  // dense index of element 0
-      const uint64_t q = k >> 2;
-      uint32_t w0[4] = {(uint32_t)q, (uint32_t)(q >> 32), step, 0u};
-      philox4x32_10(w0, seedLo, seedHi);
-      uint32_t w1[4] = {0, 0, 0, 0};
-      if (VEC == 4 && (k & 3)) {
-        const uint64_t q1 = q + 1;
-        w1[0] = (uint32_t)q1; w1[1] = (uint32_t)(q1 >> 32); w1[2] = step; w1[3] = 0u;
-        philox4x32_10(w1, seedLo, seedHi);
-      }
-      float yv[VEC];
+      const uint32_t keep = dropout_keep8((uint64_t)(firstRow + r), (uint32_t)(c >> 3), step, seedLo, seedHi, thresh16);
+      float yv[8];
 #pragma unroll
-      for (int j = 0; j < VEC; j++) {
-        const uint32_t pos = (uint32_t)(k & 3) + j;
-        const uint32_t word = (pos < 4) ? w0[pos & 3] : w1[pos & 3];
-        yv[j] = (word >= thresh) ? xv[u][j] * scale : 0.f;
-      }
-      if (full[u]) *reinterpret_cast<float4*>(y + r * ldy + c) = *reinterpret_cast<float4*>(yv);
-      else
+      for (int j = 0; j < 8; j++) yv[j] = ((keep >> j) & 1u) ? xv[u][j] * scale : 0.f;
 #pragma unroll
-        for (int j = 0; j < VEC; j++) if (c + j < H) y[r * ldy + c + j] = yv[j];
+      for (int h = 0; h < 2; h++) {
+        const int ch = c + 4 * h;
+        if (VEC == 4 && ch + 4 <= H) *reinterpret_cast<float4*>(y + r * ldy + ch) = *reinterpret_cast<float4*>(&yv[4 * h]);
+        else
+#pragma unroll
+          for (int j = 0; j < 4; j++) if (ch + j < H) y[r * ldy + ch + j] = yv[4 * h + j];
+      }
     }
   }
 }
 
-// The same mask as k_dropout, packed: bit b of mask[r][w] = keep(row r, column 32 w + b).
-// One thread builds one word from the 8 (or 9, when the word's first dense index is not a
-// multiple of 4) Philox blocks its 32 elements fall into.  Words beyond ceil(H/32) and bits
-// beyond H are written as zero so whole rows can be fetched blindly.
+// The same mask, packed: bit b of mask[r][w] = keep(row r, column 32 w + b): four Philox blocks per
+// word.  Words beyond ceil(H/32) and bits beyond H are written as zero so whole rows can be fetched
+// blindly.
 __global__ void __launch_bounds__(EW_T)
-k_dropout_mask(int64_t rows, int H, int64_t firstRow, uint32_t thresh, uint32_t seedLo, uint32_t seedHi,
+k_dropout_mask(int64_t rows, int H, int64_t firstRow, uint32_t thresh16, uint32_t seedLo, uint32_t seedHi,
                uint32_t step, uint32_t* __restrict__ mask, int64_t ldm) {
   const int Ww = (H + 31) / 32;
   const int64_t total = rows * ldm;
@@ -216,22 +226,11 @@ k_dropout_mask(int64_t rows, int H, int64_t firstRow, uint32_t thresh, uint32_t 
     const int w = (int)(i - r * ldm);
     uint32_t bits = 0u;
     if (w < Ww) {
-      const uint64_t k0 = (uint64_t)(firstRow + r) * (uint64_t)H + (uint64_t)(32 * w);
-      const int sh = (int)(k0 & 3);
-      const uint64_t q = k0 >> 2;
-      const int n = min(32, H - 32 * w);
 #pragma unroll
-      for (int b = 0; b < 9; b++) {
-        if (b == 8 && sh == 0) break;
-        const uint64_t qb = q + (uint64_t)b;
-        uint32_t c[4] = {(uint32_t)qb, (uint32_t)(qb >> 32), step, 0u};
-        philox4x32_10(c, seedLo, seedHi);
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int j = 4 * b + e - sh;
-          if ((unsigned)j < (unsigned)n && c[e] >= thresh) bits |= 1u << j;
-        }
-      }
+      for (int b = 0; b < 4; b++)
+        bits |= dropout_keep8((uint64_t)(firstRow + r), (uint32_t)(4 * w + b), step, seedLo, seedHi, thresh16) << (8 * b);
+      const int n = H - 32 * w;
+      if (n < 32) bits &= (1u << n) - 1u;
     }
     mask[i] = bits;
   }
@@ -639,14 +638,14 @@ static int dropout_launch(int64_t rows, int H, int64_t firstRow, float rate, uin
                           const float* x, int64_t ldX, float* y, int64_t ldY, cudaStream_t st) {
   if (!x || !y || rows < 0 || H <= 0 || ldX < H || ldY < H || rate < 0.f || rate >= 1.f) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
-  uint32_t thresh = dropout_thresh(rate);
+  uint32_t thresh = dropout_thresh16(rate);
   float scale = 1.0f / (1.0f - rate);
   bool vec = (ldX % 4 == 0) && (ldY % 4 == 0) && aligned16(x) && aligned16(y);
   if (vec)
-    k_dropout<4, 4><<<ew_grid((rows * ((H + 3) / 4) + 3) / 4, EW_T), EW_T, 0, st>>>(rows, H, firstRow, thresh, scale, (uint32_t)seed,
+    k_dropout<4, 2><<<ew_grid((rows * ((H + 7) / 8) + 1) / 2, EW_T), EW_T, 0, st>>>(rows, H, firstRow, thresh, scale, (uint32_t)seed,
                                                                    (uint32_t)(seed >> 32), step, x, ldX, y, ldY);
   else
-    k_dropout<1, 4><<<ew_grid((rows * H + 3) / 4, EW_T), EW_T, 0, st>>>(rows, H, firstRow, thresh, scale, (uint32_t)seed,
+    k_dropout<1, 2><<<ew_grid((rows * ((H + 7) / 8) + 1) / 2, EW_T), EW_T, 0, st>>>(rows, H, firstRow, thresh, scale, (uint32_t)seed,
                                                         (uint32_t)(seed >> 32), step, x, ldX, y, ldY);
   ROC_LAUNCH_CHECK();
   return ROC_OK;
@@ -668,7 +667,7 @@ extern "C" int roc_dropout_mask(int64_t rows, int H, int64_t firstRow, float rat
   if (!mask || rows < 0 || H <= 0 || ldMask < (H + 31) / 32 || rate < 0.f || rate >= 1.f) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
   k_dropout_mask<<<ew_grid(rows * ldMask, EW_T), EW_T, 0, as_stream(stream)>>>(
-      rows, H, firstRow, dropout_thresh(rate), (uint32_t)seed, (uint32_t)(seed >> 32), step, mask, ldMask);
+      rows, H, firstRow, dropout_thresh16(rate), (uint32_t)seed, (uint32_t)(seed >> 32), step, mask, ldMask);
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }

@@ -217,12 +217,20 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const bool masked = p.mask != nullptr;
     int s = g % p.stages; uint32_t ph = (uint32_t)(g / p.stages) & 1u;
     int kb = g % p.numKb; int64_t tile = blockIdx.x + (int64_t)(g / p.numKb) * gridDim.x;
+    // dropout fused into the operand load: bit c of mask[row][kb] keeps column 32 kb + c.  The word
+    // for this group's NEXT k-block is fetched one iteration ahead so its latency hides behind the split.
+    uint32_t mwNext = 0xFFFFFFFFu;
+    if (masked && g < iters) {
+      const int64_t row = tile * TC_BM + t;
+      mwNext = (row < p.rows) ? __ldg(p.mask + row * p.ldm + kb) : 0u;
+    }
     for (int64_t it = g; it < iters; it += p.splitGroups) {
-      // dropout fused into the operand load: bit c of mask[row][kb] keeps column 32 kb + c
-      uint32_t mw = 0xFFFFFFFFu;
-      if (masked) {
-        const int64_t row = tile * TC_BM + t;
-        mw = (row < p.rows) ? __ldg(p.mask + row * p.ldm + kb) : 0u;
+      const uint32_t mw = mwNext;
+      if (masked && it + p.splitGroups < iters) {
+        int kbN = kb + p.splitGroups; int64_t tileN = tile;
+        while (kbN >= p.numKb) { kbN -= p.numKb; tileN += gridDim.x; }
+        const int64_t rowN = tileN * TC_BM + t;
+        mwNext = (rowN < p.rows) ? __ldg(p.mask + rowN * p.ldm + kbN) : 0u;
       }
       mbar_wait(&full[s], ph);
       // 128B swizzle: 16-byte chunk j of row t sits at chunk j ^ (t & 7)

@@ -260,7 +260,7 @@ def test_activation_add():
 def test_dropout_mask_bit_exact(h, rate):
     rows, first = 257, 1000
     x = np.random.RandomState(1).randn(rows, h).astype(np.float32)
-    keep = oracle.dropout_mask(first * h, rows * h, rate, (5 << 32) | 3, 9).reshape(rows, h)
+    keep = oracle.dropout_mask(first, rows, h, rate, (5 << 32) | 3, 9)
     want = oracle.dropout_apply(x, keep, rate)
     for xin in (torch.from_numpy(x).to(DEV), K.padded(rows, h, DEV, fill=torch.from_numpy(x).to(DEV))):
         got = K.dropout_fwd(xin, first, rate, (5 << 32) | 3, 9)
@@ -270,7 +270,7 @@ def test_dropout_mask_bit_exact(h, rate):
 @pytest.mark.parametrize("h,rate", [(602, 0.5), (64, 0.5), (41, 0.1), (33, 0.9), (128, 0.5)])
 def test_dropout_packed_mask_bit_exact(h, rate):
     rows, first = 300, 12345
-    keep = oracle.dropout_mask(first * h, rows * h, rate, (7 << 32) | 1, 4).reshape(rows, h)
+    keep = oracle.dropout_mask(first, rows, h, rate, (7 << 32) | 1, 4)
     m = K.dropout_mask(rows, h, first, rate, (7 << 32) | 1, 4, DEV).cpu().numpy().view(np.uint32)
     assert m.shape[1] % 4 == 0 and m.shape[1] * 32 >= h
     bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, -1)

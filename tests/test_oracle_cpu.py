@@ -112,13 +112,31 @@ def test_linear_and_grads_match_numpy():
     assert (yr >= 0).all() and np.array_equal(yr > 0, y > 0)
 
 
-def test_dropout_mask_is_a_pure_function_of_index():
-    a = oracle.dropout_mask(0, 4096, 0.5, 7, 3)
-    b = oracle.dropout_mask(1000, 96, 0.5, 7, 3)
-    assert np.array_equal(a[1000:1096], b)
-    assert 0.4 < a.mean() < 0.6
-    assert oracle.dropout_mask(0, 64, 0.0, 1, 1).all()
-    assert not np.array_equal(a, oracle.dropout_mask(0, 4096, 0.5, 7, 4))
+def test_philox_known_answers():
+    """Philox4x32-10 against Random123's kat_vectors (Salmon et al., SC'11) — pins the dropout generator."""
+    kat = [([0, 0, 0, 0], [0, 0], "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+            "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kat:
+        assert " ".join("%08x" % v for v in oracle.philox4x32_10(ctr, key)) == want
+
+
+def test_dropout_mask_is_a_pure_function_of_row_and_column():
+    a = oracle.dropout_mask(0, 512, 41, 0.5, 7, 3)
+    b = oracle.dropout_mask(100, 12, 41, 0.5, 7, 3)
+    assert np.array_equal(a[100:112], b)                       # depends on the global row only
+    wide = oracle.dropout_mask(0, 512, 64, 0.5, 7, 3)
+    assert np.array_equal(wide[:, :41], a)                     # ... and on the column, not on the width
+    assert 0.45 < a.mean() < 0.55
+    assert oracle.dropout_mask(0, 8, 8, 0.0, 1, 1).all()
+    assert not np.array_equal(a, oracle.dropout_mask(0, 512, 41, 0.5, 7, 4))
+    # the definition, spelled out: lane (c & 7) of block (row, c >> 3), 16 bits, >= round(rate * 65536)
+    r, c, rate, seed, step = 77, 29, 0.3, (9 << 32) | 5, 11
+    o = oracle.philox4x32_10([r, 0, c >> 3, step], [seed & 0xFFFFFFFF, seed >> 32])
+    lane = c & 7
+    u16 = (int(o[lane >> 1]) >> (16 * (lane & 1))) & 0xFFFF
+    assert oracle.dropout_mask(r, 1, 64, rate, seed, step)[0, c] == (u16 >= int(rate * 65536 + 0.5))
 
 
 def test_softmax_metrics_hand_case():
