@@ -234,6 +234,17 @@ int roc_softmax_xent_bwd_idx(int64_t rows, int C, const float* logits, int64_t l
                              const int32_t* labelIdx, const int32_t* mask, float* grad,
                              int64_t ldG, roc_perf_metrics* perf, roc_stream_t stream);
 
+/* roc_softmax_xent_bwd(_idx) with the backward of the InDegreeNorm that produced the logits
+ * (gnn.cc:85 / graphnorm_kernel.cu:133) folded in: grad[v] = ((P - labels) or 0) / sqrtf(deg(v)).
+ * Exactly one of `labels` (one-hot fp32) / `labelIdx` (class index per row) is non-NULL;
+ * rowEnd is rowLeft-relative as everywhere.  Bit-identical to roc_softmax_xent_bwd followed
+ * by roc_indegree_norm on the gradient. */
+int roc_softmax_xent_bwd_norm(int64_t rows, int C, const float* logits, int64_t ldZ,
+                              const float* labels, int64_t ldL, const int32_t* labelIdx,
+                              const int32_t* mask, float* grad, int64_t ldG,
+                              const roc_eid_t* rowEnd, roc_eid_t colLeft,
+                              roc_perf_metrics* perf, roc_stream_t stream);
+
 /* --------------------------------------------------------------- Linear --- */
 
 /* Replaces cublasSgemm in Linear::forward_task, linear_kernel.cu:76-80 (+ the
@@ -279,6 +290,32 @@ int roc_linear_bwd_dropout(int64_t rows, int inDim, int outDim, const float* X, 
                            int accumulate_dX, void* workspace, size_t workspaceBytes,
                            const uint32_t* mask, int64_t ldMask, float rate,
                            roc_stream_t stream);
+
+/* roc_linear_bwd with the backward of the ops upstream of X folded into the dX epilogue,
+ * so dX is written once, already as the gradient the next ScatterGather backward reads.
+ * In model order (gnn.cc:81-88)  ... -> indegree_norm -> relu -> dropout -> linear:
+ *   dX = dY W                                           (linear_kernel.cu:227-231)
+ *   dX = keep ? dX / (1 - dropRate) : 0   if dropMask    (dropout_kernel.cu:149-150)
+ *   dX = dxReluOf > 0 ? dX : 0            if dxReluOf    (Activation backward, cudnnActivationBackward
+ *                                                         on the stored relu output, activation_kernel.cu)
+ *   dX = dX / sqrtf(deg(row))             if dxNormRowEnd (InDegreeNorm backward, graphnorm_kernel.cu:133)
+ * Zero / NULL fields switch the stage off; with all off this is roc_linear_bwd.  Each stage is
+ * bit-identical to the separate kernel it replaces. */
+typedef struct roc_linear_bwd_args {
+  int64_t rows; int inDim, outDim;
+  const float* X; int64_t ldX;
+  const float* W;
+  const float* Y; int64_t ldY;
+  float* dY; int64_t ldDY;
+  float* dW;
+  float* dX; int64_t ldDX;
+  int activation, accumulate_dX;
+  void* workspace; size_t workspaceBytes;
+  const uint32_t* dropMask; int64_t ldMask; float dropRate;
+  const float* dxReluOf; int64_t ldReluOf;
+  const roc_eid_t* dxNormRowEnd; roc_eid_t colLeft;
+} roc_linear_bwd_args;
+int roc_linear_bwd_fused(const roc_linear_bwd_args* args, roc_stream_t stream);
 
 /* ------------------------------------------------------------ optimizer --- */
 

@@ -246,6 +246,7 @@ public:
   virtual void backward(const Model& model);
   int reluMaskOf;   /* backward: also apply the relu mask of this region's values (-1: none) */
   int bwdIn;        /* region whose grad is read in backward (-1: own output) */
+  bool bwdFused;    /* backward done in another op's epilogue (a Linear's dX or the softmax) */
 };
 
 class Linear : public GnnOp {  /* gnn.h:263-285, linear.cc */
@@ -263,6 +264,10 @@ public:
   int dropOp;       /* >= 0: layers[dropOp] is the Dropout feeding this op, applied while X is loaded */
   uint32_t* dropMask;      /* packed keep-mask of that dropout, [rows][dropLd] (roc_dropout_mask) */
   int64_t dropLd;
+  /* dX epilogue fusions: relu mask of region dxReluOf's values, then / sqrt(deg); dX goes to dxOut's grad */
+  int dxReluOf;     /* -1: none */
+  bool dxNorm;
+  int dxOut;        /* -1: the input's own grad */
 };
 
 class Activation : public GnnOp {  /* gnn.h:287-302, activation.cc */
@@ -305,6 +310,7 @@ public:
   virtual void backward(const Model& model);
 public:
   int epoch_num;
+  int gradOut;      /* >= 0: write the logits' grad / sqrt(deg) into this region's grad (fused norm backward) */
 };
 
 /* CLI of the reference driver, gnn.cc:114-179 (same flags, same `-dr` quirk). */

@@ -18,6 +18,19 @@ SG_EPI_NONE, SG_EPI_NORM, SG_EPI_RELU = 0, 1, 2
 LINEAR_NORM_EPILOGUE = 1
 
 
+class LinearBwdArgs(C.Structure):
+    """roc_linear_bwd_args (include/roc_b200.h)."""
+    _fields_ = [("rows", C.c_int64), ("inDim", C.c_int), ("outDim", C.c_int),
+                ("X", C.c_void_p), ("ldX", C.c_int64), ("W", C.c_void_p),
+                ("Y", C.c_void_p), ("ldY", C.c_int64), ("dY", C.c_void_p), ("ldDY", C.c_int64),
+                ("dW", C.c_void_p), ("dX", C.c_void_p), ("ldDX", C.c_int64),
+                ("activation", C.c_int), ("accumulate_dX", C.c_int),
+                ("workspace", C.c_void_p), ("workspaceBytes", C.c_size_t),
+                ("dropMask", C.c_void_p), ("ldMask", C.c_int64), ("dropRate", C.c_float),
+                ("dxReluOf", C.c_void_p), ("ldReluOf", C.c_int64),
+                ("dxNormRowEnd", C.c_void_p), ("colLeft", C.c_uint64)]
+
+
 class PerfMetrics(C.Structure):
     """PerfMetrics, softmax_kernel.cu:35-39."""
     _fields_ = [("trainLoss", C.c_float), ("trainAll", C.c_int), ("testAll", C.c_int), ("valAll", C.c_int),
@@ -75,6 +88,8 @@ PROTOTYPES = {
     "roc_dropout_mask": (i32, [i64, i32, i64, f32, u64, u32, vp, i64, vp]),
     "roc_softmax_xent_bwd": (i32, [i64, i32, vp, i64, vp, i64, vp, vp, i64, vp, vp]),
     "roc_softmax_xent_bwd_idx": (i32, [i64, i32, vp, i64, vp, vp, vp, i64, vp, vp]),
+    "roc_softmax_xent_bwd_norm": (i32, [i64, i32, vp, i64, vp, i64, vp, vp, vp, i64, vp, u64, vp, vp]),
+    "roc_linear_bwd_fused": (i32, [vp, vp]),
     "roc_linear_fwd": (i32, [i64, i32, i32, vp, i64, vp, vp, i64, i32, i32, vp, u64, vp]),
     "roc_linear_bwd_workspace_bytes": (sz, [i64, i32, i32]),
     "roc_linear_bwd": (i32, [i64, i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, sz, vp]),

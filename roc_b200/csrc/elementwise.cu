@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256)
 k_softmax_xent(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
                const float* __restrict__ onehot, int64_t ldl, const int32_t* __restrict__ labelIdx,
                const int32_t* __restrict__ mask, float* __restrict__ g, int64_t ldg,
-               roc_perf_metrics* perf) {
+               roc_perf_metrics* perf, const uint64_t* __restrict__ rowEnd, uint64_t colLeft) {
   __shared__ float sLoss;
   __shared__ int sCnt[6];
   if (threadIdx.x == 0) sLoss = 0.f;
@@ -257,6 +257,11 @@ k_softmax_xent(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
   for (int64_t r = blockIdx.x * (int64_t)warpsPerBlock + (threadIdx.x >> 5); r < rows;
        r += (int64_t)gridDim.x * warpsPerBlock) {
     const float* zr = z + r * ldz;
+    RowDiv rd = rowdiv_make(1.0f);
+    if (rowEnd) {
+      const uint64_t st = (r == 0) ? colLeft : rowEnd[r - 1];
+      rd = rowdiv_make(sqrtf((float)(uint32_t)(rowEnd[r] - st)));
+    }
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, zr[c]);
 #pragma unroll
@@ -278,7 +283,9 @@ k_softmax_xent(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
       else lab = (c == tl) ? 1.0f : 0.0f;
       if (!ONEHOT && c == tl) trueIdx = c;
       if (trueIdx == c) pTrue = p;
-      g[r * ldg + c] = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
+      float gv = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
+      if (rowEnd) gv = rowdiv(gv, rd);     // fused InDegreeNorm backward (== gv / sqrtf(deg))
+      g[r * ldg + c] = gv;
     }
     // warp argmax: larger p wins, ties -> smaller index (what a serial first-max scan gives)
 #pragma unroll
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(256)
 k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t ldz,
                       const float* __restrict__ onehot, int64_t ldl, const int32_t* __restrict__ labelIdx,
                       const int32_t* __restrict__ mask, float* __restrict__ g, int64_t ldg,
-                      roc_perf_metrics* perf) {
+                      roc_perf_metrics* perf, const uint64_t* __restrict__ rowEnd, uint64_t colLeft) {
   __shared__ float sLoss;
   __shared__ int sCnt[6];
   if (threadIdx.x == 0) sLoss = 0.f;
@@ -338,6 +345,11 @@ k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t 
   for (int64_t r = blockIdx.x * (int64_t)rowsPerBlock + threadIdx.x / LR; r < rows;
        r += (int64_t)gridDim.x * rowsPerBlock) {
     const float* zr = z + r * ldz;
+    RowDiv rd = rowdiv_make(1.0f);
+    if (rowEnd) {
+      const uint64_t st = (r == 0) ? colLeft : rowEnd[r - 1];
+      rd = rowdiv_make(sqrtf((float)(uint32_t)(rowEnd[r] - st)));
+    }
     float v[4];
     float m = -INFINITY;
 #pragma unroll
@@ -371,7 +383,9 @@ k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t 
         if (ONEHOT) { lab = onehot[r * ldl + c]; if (lab > 0.5f) trueIdx = c; }
         else { lab = (c == tl) ? 1.0f : 0.0f; if (c == tl) trueIdx = c; }
         if (trueIdx == c) pTrue = p;
-        g[r * ldg + c] = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
+        float gv = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
+        if (rowEnd) gv = rowdiv(gv, rd);   // fused InDegreeNorm backward (== gv / sqrtf(deg))
+        g[r * ldg + c] = gv;
       }
     }
 #pragma unroll
@@ -412,15 +426,15 @@ k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t 
 template <bool ONEHOT>
 static void launch_softmax(int64_t rows, int C, const float* logits, int64_t ldZ, const float* labels, int64_t ldL,
                            const int32_t* labelIdx, const int32_t* mask, float* grad, int64_t ldG,
-                           roc_perf_metrics* perf, cudaStream_t st) {
+                           roc_perf_metrics* perf, const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st) {
   if (C <= 32) {
-    k_softmax_xent_narrow<ONEHOT, 8><<<ew_grid(rows * 8, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+    k_softmax_xent_narrow<ONEHOT, 8><<<ew_grid(rows * 8, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf, rowEnd, colLeft);
   } else if (C <= 64) {
-    k_softmax_xent_narrow<ONEHOT, 16><<<ew_grid(rows * 16, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+    k_softmax_xent_narrow<ONEHOT, 16><<<ew_grid(rows * 16, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf, rowEnd, colLeft);
   } else if (C <= 128) {
-    k_softmax_xent_narrow<ONEHOT, 32><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+    k_softmax_xent_narrow<ONEHOT, 32><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf, rowEnd, colLeft);
   } else {
-    k_softmax_xent<ONEHOT><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf);
+    k_softmax_xent<ONEHOT><<<ew_grid(rows * 32, 256), 256, 0, st>>>(rows, C, logits, ldZ, labels, ldL, labelIdx, mask, grad, ldG, perf, rowEnd, colLeft);
   }
 }
 
@@ -677,7 +691,7 @@ extern "C" int roc_softmax_xent_bwd(int64_t rows, int C, const float* logits, in
                                     roc_perf_metrics* perf, roc_stream_t stream) {
   if (!logits || !labels || !mask || !grad || rows < 0 || C <= 0 || ldZ < C || ldL < C || ldG < C) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
-  launch_softmax<true>(rows, C, logits, ldZ, labels, ldL, nullptr, mask, grad, ldG, perf, as_stream(stream));
+  launch_softmax<true>(rows, C, logits, ldZ, labels, ldL, nullptr, mask, grad, ldG, perf, nullptr, 0, as_stream(stream));
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }
@@ -689,7 +703,21 @@ extern "C" int roc_softmax_xent_bwd_idx(int64_t rows, int C, const float* logits
                                         roc_perf_metrics* perf, roc_stream_t stream) {
   if (!logits || !labelIdx || !mask || !grad || rows < 0 || C <= 0 || ldZ < C || ldG < C) return ROC_ERR_INVALID;
   if (rows == 0) return ROC_OK;
-  launch_softmax<false>(rows, C, logits, ldZ, nullptr, 0, labelIdx, mask, grad, ldG, perf, as_stream(stream));
+  launch_softmax<false>(rows, C, logits, ldZ, nullptr, 0, labelIdx, mask, grad, ldG, perf, nullptr, 0, as_stream(stream));
+  ROC_LAUNCH_CHECK();
+  return ROC_OK;
+}
+
+extern "C" int roc_softmax_xent_bwd_norm(int64_t rows, int C, const float* logits, int64_t ldZ, const float* labels,
+                                         int64_t ldL, const int32_t* labelIdx, const int32_t* mask, float* grad,
+                                         int64_t ldG, const roc_eid_t* rowEnd, roc_eid_t colLeft,
+                                         roc_perf_metrics* perf, roc_stream_t stream) {
+  if (!logits || !mask || !grad || !rowEnd || rows < 0 || C <= 0 || ldZ < C || ldG < C) return ROC_ERR_INVALID;
+  if ((labels != nullptr) == (labelIdx != nullptr)) return ROC_ERR_INVALID;   // exactly one label form
+  if (labels && ldL < C) return ROC_ERR_INVALID;
+  if (rows == 0) return ROC_OK;
+  if (labels) launch_softmax<true>(rows, C, logits, ldZ, labels, ldL, nullptr, mask, grad, ldG, perf, rowEnd, colLeft, as_stream(stream));
+  else launch_softmax<false>(rows, C, logits, ldZ, nullptr, 0, labelIdx, mask, grad, ldG, perf, rowEnd, colLeft, as_stream(stream));
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }

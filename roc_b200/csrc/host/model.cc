@@ -269,6 +269,41 @@ bool Model::init(const Config& config) {
       d->fusedInto = w.consumerOp[ro];
     }
   }
+  // ---- backward-only fusions into epilogues
+  if (fuse) {
+    Wiring w = wire(layers);
+    for (size_t l = 0; l < layers.size(); l++) {
+      // (a) ... -> indegree_norm -> softmax_cross_entropy: the softmax kernel divides the logits'
+      //     gradient by sqrt(deg) and writes it where the norm's input gradient lives
+      if (SoftmaxCrossEntropy* sce = as<SoftmaxCrossEntropy>(layers[l])) {
+        const int rz = sce->inputs[0].region;
+        if (!w.producer.count(rz) || w.consumers[rz] != 1) continue;
+        InDegreeNorm* n = as<InDegreeNorm>(layers[w.producer[rz]]);
+        if (!n || n->bwdFused || n->reluMaskOf >= 0 || n->bwdIn >= 0) continue;
+        if (n->fusedInto >= 0 && as<Linear>(layers[(size_t)n->fusedInto])) continue;   // handled by the SG epilogue
+        if (!rt->t(n->inputs[0].region).requiresGrad) continue;
+        sce->gradOut = n->inputs[0].region;
+        n->bwdFused = true;
+        continue;
+      }
+      // (b) indegree_norm -> relu -> [dropout ->] linear: the linear's dX epilogue applies the dropout
+      //     backward, the relu mask and the norm, and writes the norm's input gradient directly
+      Linear* lin = as<Linear>(layers[l]);
+      if (!lin || lin->dxOut >= 0) continue;
+      const int rin = lin->dropOp >= 0 ? layers[(size_t)lin->dropOp]->inputs[0].region : lin->inputs[0].region;
+      if (!rt->t(rin).requiresGrad || !w.producer.count(rin) || w.consumers[rin] != 1) continue;
+      Activation* act = as<Activation>(layers[w.producer[rin]]);
+      if (!act || act->actiMode != AC_MODE_RELU || act->fusedInto < 0) continue;
+      const int rn = act->inputs[0].region;
+      if (!w.producer.count(rn)) continue;
+      InDegreeNorm* n = as<InDegreeNorm>(layers[w.producer[rn]]);
+      if (!n || n->bwdFused || n->reluMaskOf != rin || n->bwdIn != rin) continue;
+      lin->dxReluOf = rin;
+      lin->dxNorm = true;
+      lin->dxOut = n->inputs[0].region;
+      n->bwdFused = true;
+    }
+  }
   for (size_t l = 0; l < layers.size(); l++) layers[l]->init(*this);
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   return true;
@@ -516,7 +551,8 @@ void ScatterGather::backward(const Model& model) {
 }
 
 // --------------------------------------------------------- InDegreeNorm -----
-InDegreeNorm::InDegreeNorm(const Model& model, const Tensor& _input) : GnnOp(_input), reluMaskOf(-1), bwdIn(-1) {
+InDegreeNorm::InDegreeNorm(const Model& model, const Tensor& _input)
+    : GnnOp(_input), reluMaskOf(-1), bwdIn(-1), bwdFused(false) {
   ROC_ASSERT(inputs[0].type == Tensor::NODE_TENSOR);   // graphnorm.cc:33-35
   ROC_ASSERT(inputs[0].numDim == 2);
   ROC_ASSERT(inputs[0].dims[1] == model.myGraph.numNodes);
@@ -541,6 +577,7 @@ void InDegreeNorm::backward(const Model& model) {
   // fused into the linear's epilogue forward => the SG backward epilogue already
   // produced d(linear out); nothing to do here
   if (fusedInto >= 0 && dynamic_cast<Linear*>(model.layers[(size_t)fusedInto])) return;
+  if (bwdFused) return;   // a Linear's dX epilogue / the softmax already wrote this gradient
   const Graph& g = model.myGraph;
   const int src = bwdIn >= 0 ? bwdIn : outputs[0].region;
   ROC_CHECK(roc_indegree_norm(g.rowLeft, g.rowRight, g.colLeft, (int)inputs[0].dims[0], g.d_rowEnd, rt->grad(src),
@@ -550,7 +587,8 @@ void InDegreeNorm::backward(const Model& model) {
 
 // ----------------------------------------------------------------- Linear ---
 Linear::Linear(const Model& model, const Tensor& _input, int outDim, ActiMode _activation, Initializer* initializer)
-    : GnnOp(_input), activation(_activation), flags(0), fwdOut(-1), bwdIn(-1), dropOp(-1), dropMask(nullptr), dropLd(0) {
+    : GnnOp(_input), activation(_activation), flags(0), fwdOut(-1), bwdIn(-1), dropOp(-1), dropMask(nullptr), dropLd(0),
+      dxReluOf(-1), dxNorm(false), dxOut(-1) {
   ROC_ASSERT(_input.numDim == 2);   // linear.cc:41-42
   ROC_ASSERT(_input.dims[1] == model.myGraph.numNodes);
   weight = model.create_weight_tensor((int)_input.dims[0], outDim, initializer);
@@ -602,26 +640,35 @@ void Linear::forward(const Model& model) {
 
 void Linear::backward(const Model& model) {
   RuntimeImpl* rt = model.ctx;
+  const Graph& g = model.myGraph;
   const int gy = bwdIn >= 0 ? bwdIn : outputs[0].region;
-  const float* Y = (activation != AC_MODE_NONE) ? rt->data(outputs[0].region) : NULL;
+  roc_linear_bwd_args a;
+  memset(&a, 0, sizeof(a));
+  int xRegion = inputs[0].region;
+  a.accumulate_dX = resetInputGrads[0] ? 0 : 1;
   if (dropOp >= 0) {
-    // dW from the masked X; dX lands directly in the gradient of the dropout's input (the
-    // dropout backward, dropout_kernel.cu:149-150, runs in the dX epilogue; it always overwrites, :119)
+    // dW from the masked X; dX lands directly in the gradient of the dropout's input (the dropout
+    // backward, dropout_kernel.cu:149-150, runs in the dX epilogue; it always overwrites, :119)
     const FusedDrop f = fused_drop(model, dropOp);
     ROC_ASSERT(resetInputGrads[0]);
-    float* dX = rt->t(f.inRegion).requiresGrad ? rt->grad(f.inRegion) : NULL;   // Q8: leaf grads skipped
-    ROC_CHECK(roc_linear_bwd_dropout(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1],
-                                     rt->data(f.inRegion), rt->t(f.inRegion).ld, rt->data(weight.region), Y,
-                                     rt->t(outputs[0].region).ld, rt->grad(gy), rt->t(gy).ld,
-                                     rt->grad(weight.region), dX, rt->t(f.inRegion).ld, (int)activation, 0,
-                                     rt->linWs, rt->linWsBytes, dropMask, dropLd, f.rate, rt->stream));
-    return;
+    xRegion = f.inRegion;
+    a.accumulate_dX = 0;
+    a.dropMask = dropMask; a.ldMask = dropLd; a.dropRate = f.rate;
   }
-  float* dX = rt->t(inputs[0].region).requiresGrad ? rt->grad(inputs[0].region) : NULL;   // Q8: leaf grads skipped
-  ROC_CHECK(roc_linear_bwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
-                           rt->t(inputs[0].region).ld, rt->data(weight.region), Y, rt->t(outputs[0].region).ld,
-                           rt->grad(gy), rt->t(gy).ld, rt->grad(weight.region), dX, rt->t(inputs[0].region).ld,
-                           (int)activation, resetInputGrads[0] ? 0 : 1, rt->linWs, rt->linWsBytes, rt->stream));
+  const int dxRegion = dxOut >= 0 ? dxOut : xRegion;
+  a.rows = model.local_rows(); a.inDim = (int)weight.dims[0]; a.outDim = (int)weight.dims[1];
+  a.X = rt->data(xRegion); a.ldX = rt->t(xRegion).ld;
+  a.W = rt->data(weight.region);
+  a.Y = (activation != AC_MODE_NONE) ? rt->data(outputs[0].region) : NULL; a.ldY = rt->t(outputs[0].region).ld;
+  a.dY = rt->grad(gy); a.ldDY = rt->t(gy).ld;
+  a.dW = rt->grad(weight.region);
+  a.dX = rt->t(xRegion).requiresGrad ? rt->grad(dxRegion) : NULL;   // Q8: leaf grads skipped
+  a.ldDX = rt->t(dxRegion).ld;
+  a.activation = (int)activation;
+  a.workspace = rt->linWs; a.workspaceBytes = rt->linWsBytes;
+  if (a.dX && dxReluOf >= 0) { a.dxReluOf = rt->data(dxReluOf); a.ldReluOf = rt->t(dxReluOf).ld; }
+  if (a.dX && dxNorm) { a.dxNormRowEnd = g.d_rowEnd; a.colLeft = g.colLeft; }
+  ROC_CHECK(roc_linear_bwd_fused(&a, rt->stream));
 }
 
 // ------------------------------------------------------------- Activation ---
@@ -708,7 +755,7 @@ void Dropout::backward(const Model& model) {
 
 // ---------------------------------------------------- SoftmaxCrossEntropy ---
 SoftmaxCrossEntropy::SoftmaxCrossEntropy(const Model&, const Tensor& _logit, const Tensor& _label, const Tensor& _mask)
-    : GnnOp(_logit, _label, _mask), epoch_num(0) {
+    : GnnOp(_logit, _label, _mask), epoch_num(0), gradOut(-1) {
   ROC_ASSERT(_logit.numDim == 2);   // softmax.cc:36-39
   ROC_ASSERT(_label.numDim == 2);
   ROC_ASSERT(_label.dims[0] == _logit.dims[0]);
@@ -733,7 +780,15 @@ void SoftmaxCrossEntropy::backward(const Model& model) {
   TensorImpl& lab = rt->t(inputs[1].region);
   ROC_CHECK(cudaMemsetAsync(rt->d_perf, 0, sizeof(roc_perf_metrics), rt->stream));
   const int32_t* mask = reinterpret_cast<const int32_t*>(rt->data(inputs[2].region));
-  if (lab.labelIdx) {
+  if (gradOut >= 0) {
+    // the logits come from an InDegreeNorm: its backward (grad / sqrt(deg)) is applied here and the
+    // result goes straight into the gradient the ScatterGather backward reads
+    const Graph& g = model.myGraph;
+    ROC_CHECK(roc_softmax_xent_bwd_norm(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
+                                        lab.labelIdx ? NULL : rt->data(inputs[1].region), lab.labelIdx ? 0 : lab.ld,
+                                        lab.labelIdx, mask, rt->grad(gradOut), rt->t(gradOut).ld, g.d_rowEnd,
+                                        g.colLeft, rt->d_perf, rt->stream));
+  } else if (lab.labelIdx) {
     ROC_CHECK(roc_softmax_xent_bwd_idx(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
                                        lab.labelIdx, mask, rt->grad(inputs[0].region), rt->t(inputs[0].region).ld,
                                        rt->d_perf, rt->stream));

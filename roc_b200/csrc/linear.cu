@@ -9,7 +9,8 @@ int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t
                     int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
                     cudaStream_t st);
 int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                   int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st);
+                   int64_t ldDX, int accumulate, const DropMask* dm, const float* reluOf, int64_t ldR,
+                   const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
 int simt_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
                    float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st);
 int relu_bwd_inplace(int64_t rows, int H, const float* Y, int64_t ldY, float* dY, int64_t ldDY, cudaStream_t st);
@@ -20,7 +21,8 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
                   int64_t ldY, int relu, const uint64_t* rowEnd, uint64_t colLeft, const DropMask* dm,
                   cudaStream_t st);
 int tc_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                 int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st);
+                 int64_t ldDX, int accumulate, const DropMask* dm, const float* reluOf, int64_t ldR,
+                 const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st);
 size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim);
 int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* dY, int64_t ldDY,
                  float* dW, float* workspace, size_t wsBytes, const DropMask* dm, cudaStream_t st);
@@ -89,7 +91,10 @@ extern "C" size_t roc_linear_bwd_workspace_bytes(int64_t rows, int inDim, int ou
 static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX, const float* W,
                            const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
                            int64_t ldDX, int activation, int accumulate_dX, void* workspace,
-                           size_t workspaceBytes, const DropMask* dm, roc_stream_t stream) {
+                           size_t workspaceBytes, const DropMask* dm, const float* dxReluOf, int64_t ldReluOf,
+                           const roc_eid_t* dxRowEnd, roc_eid_t colLeft, roc_stream_t stream) {
+  if ((dxReluOf || dxRowEnd) && !dX) return ROC_ERR_INVALID;
+  if (dxReluOf && ldReluOf < inDim) return ROC_ERR_INVALID;
   if (!X || !W || !dY || !dW || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldDY < outDim)
     return ROC_ERR_INVALID;
   if (dX && ldDX < inDim) return ROC_ERR_INVALID;
@@ -110,9 +115,12 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
   if (rc != ROC_OK) return rc;
   if (dX) {
     rc = ROC_ERR_UNSUPPORTED;
-    if (!force_simt()) rc = tc_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
+    if (!force_simt())
+      rc = tc_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, dxReluOf, ldReluOf, dxRowEnd,
+                        colLeft, st);
     if (rc == ROC_ERR_UNSUPPORTED)
-      rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, st);
+      rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, dxReluOf, ldReluOf, dxRowEnd,
+                          colLeft, st);
     if (rc != ROC_OK) return rc;
   }
   return ROC_OK;
@@ -123,7 +131,7 @@ extern "C" int roc_linear_bwd(int64_t rows, int inDim, int outDim, const float* 
                               int64_t ldDX, int activation, int accumulate_dX, void* workspace,
                               size_t workspaceBytes, roc_stream_t stream) {
   return linear_bwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, dY, ldDY, dW, dX, ldDX, activation, accumulate_dX,
-                         workspace, workspaceBytes, nullptr, stream);
+                         workspace, workspaceBytes, nullptr, nullptr, 0, nullptr, 0, stream);
 }
 
 extern "C" int roc_linear_bwd_dropout(int64_t rows, int inDim, int outDim, const float* X, int64_t ldX,
@@ -135,5 +143,19 @@ extern "C" int roc_linear_bwd_dropout(int64_t rows, int inDim, int outDim, const
   int rc = mask_args(mask, ldMask, rate, inDim, &dm, &use);
   if (rc != ROC_OK) return rc;
   return linear_bwd_impl(rows, inDim, outDim, X, ldX, W, Y, ldY, dY, ldDY, dW, dX, ldDX, activation, accumulate_dX,
-                         workspace, workspaceBytes, use, stream);
+                         workspace, workspaceBytes, use, nullptr, 0, nullptr, 0, stream);
+}
+
+// Everything roc_linear_bwd / roc_linear_bwd_dropout do, plus the backward of the ops that sit
+// between X's producer and this Linear folded into the dX epilogue (see roc_linear_bwd_args).
+extern "C" int roc_linear_bwd_fused(const roc_linear_bwd_args* a, roc_stream_t stream) {
+  if (!a) return ROC_ERR_INVALID;
+  DropMask dm; const DropMask* use = nullptr;
+  if (a->dropMask || a->dropRate != 0.f) {
+    int rc = mask_args(a->dropMask, a->ldMask, a->dropRate, a->inDim, &dm, &use);
+    if (rc != ROC_OK) return rc;
+  }
+  return linear_bwd_impl(a->rows, a->inDim, a->outDim, a->X, a->ldX, a->W, a->Y, a->ldY, a->dY, a->ldDY, a->dW,
+                         a->dX, a->ldDX, a->activation, a->accumulate_dX, a->workspace, a->workspaceBytes, use,
+                         a->dxReluOf, a->ldReluOf, a->dxNormRowEnd, a->colLeft, stream);
 }

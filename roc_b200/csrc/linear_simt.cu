@@ -29,6 +29,7 @@ struct GemmP {
   // fused dropout (NULL = none): maskOn 1 = A element (m, k) [fwd], 2 = B element (k, n) [dW],
   // 3 = C element (m, n) [dX: the dropout backward]
   const uint32_t* mask; int64_t ldm; float mscale; int maskOn;
+  const float* reluOf; int64_t ldR;   // epilogue relu backward: reluOf(m, n) > 0 ? v : 0 (NULL = none)
 };
 
 template <bool A_KCONTIG, bool B_KCONTIG>
@@ -107,8 +108,10 @@ k_sgemm(const GemmP p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       if (p.relu) v = relu_nanprop(v);   // reference order: sgemm -> relu (linear_kernel.cu:83-104)
-      if (p.rowEnd) v = v / d;           // then the model's indegree_norm (gnn.cc:82)
+      // dX only: dropout backward, relu backward, then indegree-norm backward (the ops upstream of X)
       if (p.maskOn == 3) v = drop_apply(p.mask, p.ldm, p.mscale, m, n, v);
+      if (p.reluOf) v = (p.reluOf[m * p.ldR + n] > 0.f) ? v : 0.f;
+      if (p.rowEnd) v = v / d;           // fwd: the model's indegree_norm (gnn.cc:82)
       float* dst = C + m * p.ldc + n;
       *dst = p.accumulate ? *dst + v : v;
     }
@@ -167,11 +170,13 @@ int simt_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t
 }
 
 int simt_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                   int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st) {
+                   int64_t ldDX, int accumulate, const DropMask* dm, const float* reluOf, int64_t ldR,
+                   const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st) {
   GemmP p{};
   p.A = dY; p.lda = ldDY; p.B = W; p.ldb = inDim; p.C = dX; p.ldc = ldDX;
   p.M = rows; p.N = inDim; p.K = outDim; p.kPerSplit = outDim; p.accumulate = accumulate;
   set_mask(p, dm, 3);
+  p.reluOf = reluOf; p.ldR = ldR; p.rowEnd = rowEnd; p.colLeft = colLeft;
   dim3 grid((unsigned)((rows + GB_M - 1) / GB_M), (unsigned)((inDim + GB_N - 1) / GB_N), 1);
   k_sgemm<true, false><<<grid, G_THREADS, 0, st>>>(p);
   ROC_LAUNCH_CHECK();

@@ -36,7 +36,7 @@ using namespace tc;
 constexpr int TC_BM = 128;       // rows per tile (UMMA M)
 constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
 constexpr int TC_UK = 8;         // UMMA K for tf32
-constexpr int TS_THREADS = 512;  // launched with 384 when splitGroups == 1
+constexpr int TS_THREADS = 512;  // 4 control warps + 4 x splitGroups split warps + epiWarps epilogue warps
 constexpr int TS_MAX_STAGES = 6;
 
 // Whi/Wlo[n][k] (n < Npad, k < Kpad, zero padded) = split of B(n, k), where
@@ -60,6 +60,7 @@ struct TcTsParams {
   int64_t rows; int outDim; int BN; int numKb; int stages;
   uint32_t tmemCols, dStride, aCol0;
   int splitGroups;      // 1 or 2 warpgroups of split warps (alternate k-blocks)
+  int epiWarps;         // 4 or 8 epilogue warps (8: two warps per TMEM lane quarter alternate 32-column chunks)
   const uint32_t* mask; int64_t ldm; float mscale;      // dropout of A fused into the operand load (NULL = none)
   // epilogue, applied in this order to acc(row, col):
   int relu;                                             //   relu (Linear's activation, linear_kernel.cu:83-104)
@@ -67,14 +68,25 @@ struct TcTsParams {
   const float* reluOf; int64_t ldR;                     //   relu backward: reluOf(row, col) > 0 ? x : 0
   const uint64_t* rowEnd; uint64_t colLeft;             //   indegree norm: x / sqrtf(deg(row))
   int accumulate;                                       //   Y += x instead of Y = x
+  int epiStaged;        // transpose the accumulator through smem for row-coalesced global accesses
 };
 
-__device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t row, const TcTsParams& p) {
-  float d = 1.0f;
-  if (p.rowEnd && row < p.rows) {
-    uint64_t st = (row == 0) ? p.colLeft : p.rowEnd[row - 1];
-    d = sqrtf((float)(uint32_t)(p.rowEnd[row] - st));
-  }
+// Epilogue stage switches: compile-time when the kernel is instantiated for a fixed combination
+// (EPI >= 0, a bit mask), read from the parameters for the generic instantiation (EPI < 0).  With all
+// five stages dynamic the unrolled epilogue was ~2000 SASS instructions and the epilogue warps stalled
+// on instruction fetch (r1 run 29).
+enum { EPI_RELU = 1, EPI_OMASK = 2, EPI_RELUOF = 4, EPI_NORM = 8, EPI_ACC = 16 };
+#define EPI_FLAGS(EPI, p)                                                        \
+  const bool fRelu = (EPI) < 0 ? (p).relu != 0 : ((EPI) & EPI_RELU) != 0;         \
+  const bool fOmask = (EPI) < 0 ? (p).omask != nullptr : ((EPI) & EPI_OMASK) != 0; \
+  const bool fReluOf = (EPI) < 0 ? (p).reluOf != nullptr : ((EPI) & EPI_RELUOF) != 0; \
+  const bool fNorm = (EPI) < 0 ? (p).rowEnd != nullptr : ((EPI) & EPI_NORM) != 0;  \
+  const bool fAcc = (EPI) < 0 ? (p).accumulate != 0 : ((EPI) & EPI_ACC) != 0;
+
+// Direct epilogue: each lane writes its own row (32 rows x 16 B per store instruction).
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t row, const TcTsParams& p, float d) {
+  EPI_FLAGS(EPI, p)
   const RowDiv rd = rowdiv_make(d);
   for (int c0 = 0; c0 < p.BN; c0 += 16) {
     uint32_t r[16];
@@ -84,19 +96,19 @@ __device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t
     if (row < p.rows && col0 < p.outDim) {
       float* y = p.Y + row * p.ldY + col0;
       uint32_t mw = 0xFFFFFFFFu;      // the 16 columns of this chunk lie in one mask word (col0 % 16 == 0)
-      if (p.omask) mw = __ldg(p.omask + row * p.oldm + (col0 >> 5)) >> (col0 & 31);
+      if (fOmask) mw = __ldg(p.omask + row * p.oldm + (col0 >> 5)) >> (col0 & 31);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int c = col0 + q * 4;
         const bool full = c + 4 <= p.outDim;
         float v[4], old[4] = {0.f, 0.f, 0.f, 0.f}, ro[4] = {1.f, 1.f, 1.f, 1.f};
-        if (p.accumulate) {
+        if (fAcc) {
           if (full) *reinterpret_cast<float4*>(old) = *reinterpret_cast<const float4*>(y + q * 4);
           else
 #pragma unroll
             for (int k = 0; k < 4; k++) if (c + k < p.outDim) old[k] = y[q * 4 + k];
         }
-        if (p.reluOf) {
+        if (fReluOf) {
           const float* rp = p.reluOf + row * p.ldR + c;
           if (full) *reinterpret_cast<float4*>(ro) = __ldg(reinterpret_cast<const float4*>(rp));
           else
@@ -106,11 +118,11 @@ __device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           float x = __uint_as_float(r[q * 4 + k]);
-          if (p.relu) x = relu_nanprop(x);
-          if (p.omask) x = ((mw >> (q * 4 + k)) & 1u) ? x * p.oscale : 0.f;
-          if (p.reluOf) x = (ro[k] > 0.f) ? x : 0.f;
-          if (p.rowEnd) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
-          if (p.accumulate) x = old[k] + x;
+          if (fRelu) x = relu_nanprop(x);
+          if (fOmask) x = ((mw >> (q * 4 + k)) & 1u) ? x * p.oscale : 0.f;
+          if (fReluOf) x = (ro[k] > 0.f) ? x : 0.f;
+          if (fNorm) x = rowdiv(x, rd);   // == x / d bit for bit (common.cuh)
+          if (fAcc) x = old[k] + x;
           v[k] = x;
         }
         if (full) *reinterpret_cast<float4*>(y + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
@@ -122,6 +134,116 @@ __device__ __forceinline__ void tc_epilogue_rows(uint32_t taddr, int n0, int64_t
   }
 }
 
+// Epilogue of one warp's 32 rows of a tile.  tcgen05.ld hands each lane ITS row (lane = TMEM
+// lane); written straight to global that is 32 rows x 16 B per instruction.  So each 32-column
+// chunk is transposed through a padded shared tile ([32][36] floats per warp) and then handled
+// with 8 lanes per row: every global access (Y, the accumulate read, reluOf) is a 128-byte row
+// segment, and the per-row scalars (norm divisor, dropout-mask word) are shared by the row's lanes.
+constexpr int EPI_LD = 36;                        // padded row of the transposition tile: 16-byte aligned, conflict-free
+constexpr int EPI_STG_FLOATS = 32 * EPI_LD + 32; // per warp: transposition tile + per-row divisors
+
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_warp(uint32_t taddr, int n0, int64_t row0, const TcTsParams& p,
+                                                 float* stg, int lane, float myD, int chunk0, int chunkStep) {
+  EPI_FLAGS(EPI, p)
+  float* sd = stg + 32 * EPI_LD;
+  sd[lane] = myD;     // this lane's row divisor (computed by the caller before the accumulator wait)
+  const int rq = lane >> 3, cq = (lane & 7) * 4;
+  for (int c0 = chunk0 * 32; c0 < p.BN; c0 += chunkStep * 32) {
+    const int cw = min(32, p.BN - c0);     // 32, or 16 for the last chunk of BN % 32 == 16
+    uint32_t r[32];
+    tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+    if (cw == 32) tmem_ld16(taddr + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    tmem_ld_wait();
+    __syncwarp();                           // the previous chunk's readers are done with the tile
+#pragma unroll
+    for (int k = 0; k < 32; k += 4)
+      if (k < cw)
+        *reinterpret_cast<uint4*>(stg + lane * EPI_LD + k) = make_uint4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+    __syncwarp();
+    const int c = n0 + c0 + cq;             // global column of this lane's 4 values
+    if (cq < cw && c < p.outDim) {
+      const bool full = c + 4 <= p.outDim;
+      // two batches of 4 rows: every load of a batch is issued before its arithmetic
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        float acc[4][4], old[4][4], ro[4][4], dd[4];
+        uint32_t mw[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int rl = (hb * 4 + i) * 4 + rq;
+          const int64_t row = row0 + rl;
+          const bool ok = row < p.rows;
+          *reinterpret_cast<float4*>(acc[i]) = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + cq);
+          dd[i] = fNorm ? sd[rl] : 1.0f;
+          mw[i] = 0xFu;                   // c % 4 == 0: the 4 mask bits sit in one word
+          if (fOmask && ok) mw[i] = __ldg(p.omask + row * p.oldm + (c >> 5)) >> (c & 31);
+#pragma unroll
+          for (int k = 0; k < 4; k++) { old[i][k] = 0.f; ro[i][k] = 1.f; }
+          if (fAcc && ok) {
+            const float* y = p.Y + row * p.ldY + c;
+            if (full) *reinterpret_cast<float4*>(old[i]) = *reinterpret_cast<const float4*>(y);
+            else
+#pragma unroll
+              for (int k = 0; k < 4; k++) if (c + k < p.outDim) old[i][k] = y[k];
+          }
+          if (fReluOf && ok) {
+            const float* rp = p.reluOf + row * p.ldR + c;
+            if (full) *reinterpret_cast<float4*>(ro[i]) = __ldg(reinterpret_cast<const float4*>(rp));
+            else
+#pragma unroll
+              for (int k = 0; k < 4; k++) if (c + k < p.outDim) ro[i][k] = rp[k];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int rl = (hb * 4 + i) * 4 + rq;
+          const int64_t row = row0 + rl;
+          if (row >= p.rows) continue;
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            float x = acc[i][k];
+            if (fRelu) x = relu_nanprop(x);
+            if (fOmask) x = x * p.oscale;       // the kept value; dropped ones are zeroed after the divide
+            v[k] = x;
+          }
+          // x / d first, masks after: (m ? x : 0) / d == m ? x / d : 0 bit for bit for a finite d > 0, and
+          // the divide then never sees the masked-out zeros.  Degenerate divisors (deg 0 -> 0 / 0 = NaN must
+          // survive) keep the literal order.
+          const RowDiv rd = rowdiv_make(dd[i]);
+          const bool maskFirst = fNorm && rd.plain;
+#pragma unroll
+          for (int pass = 0; pass < 2; pass++) {
+            if (pass == (maskFirst ? 0 : 1)) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                float x = v[k];
+                if (fOmask) x = ((mw[i] >> k) & 1u) ? x : 0.f;
+                if (fReluOf) x = (ro[i][k] > 0.f) ? x : 0.f;
+                v[k] = x;
+              }
+            } else if (fNorm) {
+              rowdiv4(v, rd, full ? 4 : p.outDim - c);
+            }
+          }
+          if (fAcc) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = old[i][k] + v[k];
+          }
+          float* y = p.Y + row * p.ldY + c;
+          if (full) *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
+          else
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (c + k < p.outDim) y[k] = v[k];
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWhi,
                    const __grid_constant__ CUtensorMap mapWlo, const TcTsParams p) {
@@ -137,6 +259,7 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   uint64_t* dFull = empty + TS_MAX_STAGES;                  // [2] accumulator complete
   uint64_t* dEmpty = dFull + 2;                             // [2] accumulator drained by the epilogue
   uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(dEmpty + 2);
+  float* epiStg = reinterpret_cast<float*>(barBase + 256);   // 4 warps x EPI_STG_FLOATS
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int64_t numTiles = (p.rows + TC_BM - 1) / TC_BM;
@@ -145,7 +268,7 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapWhi); tma_prefetch_desc(&mapWlo);
     for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&aFull[s], 4); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&dFull[b], 1); mbar_init(&dEmpty[b], 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(&dFull[b], 1); mbar_init(&dEmpty[b], (uint32_t)p.epiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmemAddr, p.tmemCols);
@@ -267,11 +390,21 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     uint32_t tl = 0;
     for (int64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, tl++) {
       const uint32_t b = tl & 1u;
+      // the row's norm divisor is fetched BEFORE waiting for the accumulator: its DRAM latency
+      // (rowEnd streams, always cold) then overlaps the main loop instead of adding to every tile
+      const int64_t row0 = tile * TC_BM + (warp & 3) * 32;
+      float myD = 1.0f;
+      if (p.rowEnd && row0 + lane < p.rows) {
+        const int64_t myRow = row0 + lane;
+        const uint64_t st = (myRow == 0) ? p.colLeft : p.rowEnd[myRow - 1];
+        myD = sqrtf((float)(uint32_t)(p.rowEnd[myRow] - st));
+      }
       mbar_wait(&dFull[b], (tl >> 1) & 1u);
       tc_fence_after();
-      const int64_t row = tile * TC_BM + (warp & 3) * 32 + lane;
       const uint32_t taddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16) + b * p.dStride;
-      tc_epilogue_rows(taddr, n0, row, p);
+      const int e = warp - 4 - 4 * p.splitGroups;      // epilogue warp index; warps e and e + 4 share a lane quarter
+      if (p.epiStaged) tc_epilogue_warp<EPI>(taddr, n0, row0, p, epiStg + e * EPI_STG_FLOATS, lane, myD, e >> 2, p.epiWarps >> 2);
+      else if (e < 4) tc_epilogue_rows<EPI>(taddr, n0, row0 + lane, p, myD);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dEmpty[b]);
@@ -328,30 +461,51 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   const size_t stageBytes = (size_t)TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
   int stages = (int)((512 - 2 * dStride) / 64);
   if (stages > TS_MAX_STAGES) stages = TS_MAX_STAGES;
-  while (stages > 0 && (size_t)stages * stageBytes + 1024 + 256 > (size_t)220 * 1024) stages--;
+  const size_t fixedBytes = 1024 /*align*/ + 256 /*barriers*/ + (size_t)8 * EPI_STG_FLOATS * sizeof(float);
+  while (stages > 0 && (size_t)stages * stageBytes + fixedBytes > (size_t)224 * 1024) stages--;
   if (stages < 3) return ROC_ERR_UNSUPPORTED;
   TcTsParams q{};
   q.Y = Y; q.ldY = ldY; q.rows = rows; q.outDim = N; q.BN = BN; q.numKb = Kpad / TC_BK;
   q.stages = stages; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
-  { const char* s2 = getenv("ROC_TS_SPLIT"); q.splitGroups = (s2 && s2[0] == '1') ? 1 : 2; }
+  q.accumulate = e.accumulate;
+  { const char* ee = getenv("ROC_TS_EPI"); q.epiStaged = ee ? (ee[0] == 's') : 1; }
+  // few k-blocks per tile (K <= 128): the epilogue, not the main loop, paces the kernel -> 8 epilogue
+  // warps and one split group; otherwise two split groups and 4 epilogue warps.  512 threads either way.
+  q.splitGroups = (Kpad / TC_BK <= 4 && q.epiStaged) ? 1 : 2;
+  { const char* s2 = getenv("ROC_TS_SPLIT"); if (s2) q.splitGroups = (s2[0] == '1') ? 1 : 2; }
+  if (!q.epiStaged) q.splitGroups = 2;
+  q.epiWarps = 12 - 4 * q.splitGroups;
   if (inMask) { q.mask = inMask->bits; q.ldm = inMask->ld; q.mscale = inMask->scale; }
   q.relu = e.relu;
   if (e.outMask) { q.omask = e.outMask->bits; q.oldm = e.outMask->ld; q.oscale = e.outMask->scale; }
   q.reluOf = e.reluOf; q.ldR = e.ldR;
   q.rowEnd = e.rowEnd; q.colLeft = e.colLeft;
-  q.accumulate = e.accumulate;
-  const size_t smemBytes = (size_t)stages * stageBytes + 1024 + 256;
-  static size_t configured = 0;
-  if (smemBytes > configured) {
-    ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    configured = smemBytes;
-  }
+  const size_t smemBytes = (size_t)stages * stageBytes + fixedBytes;
   const int64_t numTiles = (rows + TC_BM - 1) / TC_BM;
   int gx = sm_count() / nTiles;
   if (gx < 1) gx = 1;
   if (numTiles < gx) gx = (int)numTiles;
   dim3 grid((unsigned)gx, (unsigned)nTiles, 1);
-  k_tc_linear_ts<<<grid, 256 + 128 * q.splitGroups, smemBytes, st>>>(mapA, mapWhi, mapWlo, q);
+  const int epi = (q.relu ? EPI_RELU : 0) | (q.omask ? EPI_OMASK : 0) | (q.reluOf ? EPI_RELUOF : 0) |
+                  (q.rowEnd ? EPI_NORM : 0) | (q.accumulate ? EPI_ACC : 0);
+  const unsigned threads = TS_THREADS;
+#define ROC_TS_LAUNCH(E)                                                                                          \
+  do {                                                                                                            \
+    static size_t configured = 0;                                                                                 \
+    if (smemBytes > configured) {                                                                                 \
+      ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_ts<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes)); \
+      configured = smemBytes;                                                                                     \
+    }                                                                                                             \
+    k_tc_linear_ts<E><<<grid, threads, smemBytes, st>>>(mapA, mapWhi, mapWlo, q);                                 \
+  } while (0)
+  switch (epi) {   // the combinations the GCN path produces; anything else takes the generic kernel
+    case 0: ROC_TS_LAUNCH(0); break;
+    case EPI_NORM: ROC_TS_LAUNCH(EPI_NORM); break;
+    case EPI_OMASK: ROC_TS_LAUNCH(EPI_OMASK); break;
+    case EPI_OMASK | EPI_RELUOF | EPI_NORM: ROC_TS_LAUNCH(EPI_OMASK | EPI_RELUOF | EPI_NORM); break;
+    default: ROC_TS_LAUNCH(-1); break;
+  }
+#undef ROC_TS_LAUNCH
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }
@@ -366,9 +520,11 @@ int tc_linear_fwd(int64_t rows, int inDim, int outDim, const float* X, int64_t l
 
 // dX (+)= dY W, optionally followed in the epilogue by the dropout backward of X's producer
 int tc_linear_dx(int64_t rows, int inDim, int outDim, const float* dY, int64_t ldDY, const float* W, float* dX,
-                 int64_t ldDX, int accumulate, const DropMask* dm, cudaStream_t st) {
+                 int64_t ldDX, int accumulate, const DropMask* dm, const float* reluOf, int64_t ldR,
+                 const uint64_t* rowEnd, uint64_t colLeft, cudaStream_t st) {
   TsEpilogue e;
   e.outMask = dm; e.accumulate = accumulate;
+  e.reluOf = reluOf; e.ldR = ldR; e.rowEnd = rowEnd; e.colLeft = colLeft;
   return ts_gemm(rows, outDim, inDim, dY, ldDY, W, inDim, 1, dX, ldDX, nullptr, e, st);
 }
 

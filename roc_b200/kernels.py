@@ -208,6 +208,41 @@ def linear_bwd_dropout(x, w, y, dy, dw, mask, rate, dx=None, activation=0, accum
     return dw, dx
 
 
+def linear_bwd_fused(x, w, y, dy, dw, dx, activation=0, mask=None, rate=0.0, relu_of=None, norm_row_end=None,
+                     col_left=0):
+    """roc_linear_bwd_fused: dX epilogue = dropout backward -> relu mask (relu_of > 0) -> / sqrt(deg)."""
+    ws_bytes = lib.roc_linear_bwd_workspace_bytes(x.shape[0], x.shape[1], w.shape[0])
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    a = _lib.LinearBwdArgs()
+    a.rows, a.inDim, a.outDim = x.shape[0], x.shape[1], w.shape[0]
+    a.X, a.ldX, a.W = x.data_ptr(), _ld(x), w.data_ptr()
+    a.Y, a.ldY = (y.data_ptr(), _ld(y)) if y is not None else (None, 0)
+    a.dY, a.ldDY, a.dW = dy.data_ptr(), _ld(dy), dw.data_ptr()
+    a.dX, a.ldDX = dx.data_ptr(), _ld(dx)
+    a.activation, a.accumulate_dX = activation, 0
+    a.workspace, a.workspaceBytes = ws.data_ptr(), ws_bytes
+    if mask is not None:
+        a.dropMask, a.ldMask = mask.data_ptr(), mask.stride(0)
+    a.dropRate = rate
+    if relu_of is not None:
+        a.dxReluOf, a.ldReluOf = relu_of.data_ptr(), _ld(relu_of)
+    if norm_row_end is not None:
+        a.dxNormRowEnd, a.colLeft = norm_row_end.data_ptr(), col_left
+    check(lib.roc_linear_bwd_fused(C.byref(a), _stream()), "roc_linear_bwd_fused")
+    return dw, dx
+
+
+def softmax_xent_bwd_norm(logits, labels, mask, row_end, col_left=0, compact=False):
+    """softmax_xent_bwd with the logits' InDegreeNorm backward fused: grad rows divided by sqrt(deg)."""
+    g = torch.empty_like(logits)
+    perf = torch.zeros(7, dtype=torch.int32, device=logits.device)
+    check(lib.roc_softmax_xent_bwd_norm(logits.shape[0], logits.shape[1], _ptr(logits), _ld(logits),
+                                        None if compact else _ptr(labels), 0 if compact else _ld(labels),
+                                        _ptr(labels) if compact else None, _ptr(mask), _ptr(g), _ld(g),
+                                        _ptr(row_end), col_left, _ptr(perf), _stream()), "roc_softmax_xent_bwd_norm")
+    return g
+
+
 def linear_bwd(x, w, y, dy, dw, dx=None, activation=0, accumulate_dx=False):
     ws_bytes = lib.roc_linear_bwd_workspace_bytes(x.shape[0], x.shape[1], w.shape[0])
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)

@@ -59,6 +59,21 @@ def main():
         byt = n * (i + o) * 4
         print(json.dumps({"op": "linear_fwd", "shape": shp, "rows": n, "ms": round(ms, 4),
                           "GBps": round(byt / ms / 1e6, 1), "max_rel_err": err}), flush=True)
+        # ---- forward with the indegree-norm epilogue, and the fused dX (dropout bwd + relu mask + norm)
+        re = torch.cumsum(torch.randint(1, 30, (n,), device=dev, generator=g), 0)
+        ms = timeit(lambda: K.linear_fwd(x[:, :i], w, norm_row_end=re, out=y[:, :o]), a.iters)
+        print(json.dumps({"op": "linear_fwd+norm", "shape": shp, "rows": n, "ms": round(ms, 4),
+                          "GBps": round(byt / ms / 1e6, 1)}), flush=True)
+        if i <= 256:
+            mask = K.dropout_mask(n, i, 0, 0.5, 5, 1, dev)
+            dxb, dwb = K.padded(n, i, dev), torch.zeros(o, i, device=dev)
+            gy = K.padded(n, o, dev, fill=dy[:, :o])
+            t0 = timeit(lambda: K.linear_bwd_fused(x[:, :i], w, None, gy, dwb, dxb, mask=mask, rate=0.5,
+                                                   relu_of=x[:, :i], norm_row_end=re), a.iters)
+            t1 = timeit(lambda: K.linear_bwd(x[:, :i], w, None, gy, dwb), a.iters)
+            print(json.dumps({"op": "linear_dx_fused(bwd - dW-only bwd)", "shape": shp, "rows": n,
+                              "ms": round(t0 - t1, 4)}), flush=True)
+            del mask, dxb, gy
         # ---- dW (dX not requested)
         dw = torch.zeros(o, i, device=dev)
 

@@ -306,6 +306,48 @@ def test_linear_with_fused_dropout_matches_unfused_bitwise(n, i, o, rate):
         assert torch.equal(dx0, dx1), "dX"
 
 
+@pytest.mark.parametrize("n,i,o", [(1000, 64, 41), (4099, 200, 16), (300, 16, 16), (50, 5, 3)])
+@pytest.mark.parametrize("rate", [0.5, 0.0])
+def test_linear_bwd_fused_epilogue_matches_separate_kernels_bitwise(n, i, o, rate):
+    """dX epilogue (dropout backward -> relu mask -> / sqrt(deg)) == the three separate kernels."""
+    r = np.random.RandomState(n + o)
+    row_end = np.cumsum(r.randint(1, 9, size=n)).astype(np.uint64)
+    d_re = torch.from_numpy(row_end.view(np.int64)).to(DEV)
+    first, seed, step = 0, (1 << 32) | 7, 3
+    x = K.padded(n, i, DEV, fill=torch.from_numpy(np.maximum(r.randn(n, i), 0).astype(np.float32)).to(DEV))  # a relu output
+    w = torch.from_numpy((r.randn(o, i) * 0.1).astype(np.float32)).to(DEV)
+    dy = torch.from_numpy(r.randn(n, o).astype(np.float32)).to(DEV)
+    mask = K.dropout_mask(n, i, first, rate, seed, step, DEV) if rate > 0 else None
+    # separate: linear bwd (+dropout bwd) -> indegree_norm with relu mask
+    g0 = K.padded(n, o, DEV, fill=dy)
+    dw0, dxa = torch.zeros_like(w), K.padded(n, i, DEV)
+    K.linear_bwd_dropout(x, w, None, g0, dw0, mask, rate, dx=dxa)
+    dx0 = K.indegree_norm(0, n - 1, 0, d_re, dxa, relu_mask_of=x)
+    # fused
+    g1 = K.padded(n, o, DEV, fill=dy)
+    dw1, dx1 = torch.zeros_like(w), K.padded(n, i, DEV)
+    K.linear_bwd_fused(x, w, None, g1, dw1, dx1, mask=mask, rate=rate, relu_of=x, norm_row_end=d_re, col_left=0)
+    assert torch.equal(dw0, dw1), "dW"
+    assert torch.equal(dx0, dx1), "dX"
+
+
+def test_softmax_with_fused_norm_backward_bitwise():
+    r = np.random.RandomState(14)
+    for n, c in ((3000, 41), (500, 7), (257, 100), (64, 300)):
+        row_end = np.cumsum(r.randint(1, 20, size=n)).astype(np.uint64)
+        d_re = torch.from_numpy(row_end.view(np.int64)).to(DEV)
+        logits = K.padded(n, c, DEV, fill=torch.from_numpy((r.randn(n, c) * 2).astype(np.float32)).to(DEV))
+        lab = torch.from_numpy(r.randint(0, c, size=n).astype(np.int32)).to(DEV)
+        mask = torch.from_numpy(r.randint(0, 4, size=n).astype(np.int32)).to(DEV)
+        g, _ = K.softmax_xent_bwd(logits, lab, mask, compact=True)
+        want = K.indegree_norm(0, n - 1, 0, d_re, g)
+        got = K.softmax_xent_bwd_norm(logits, lab, mask, d_re, 0, compact=True)
+        assert torch.equal(got, want)
+        oh = torch.from_numpy(datasets.onehot(lab.cpu().numpy(), c)).to(DEV)
+        got2 = K.softmax_xent_bwd_norm(logits, oh, mask, d_re, 0, compact=False)
+        assert torch.equal(got2, want)
+
+
 def test_softmax_xent_both_label_forms():
     r = np.random.RandomState(4)
     for n, c in ((500, 7), (1000, 41), (64, 47), (10, 1)):
