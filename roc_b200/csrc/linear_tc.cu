@@ -399,10 +399,35 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         const uint64_t st = (myRow == 0) ? p.colLeft : p.rowEnd[myRow - 1];
         myD = sqrtf((float)(uint32_t)(p.rowEnd[myRow] - st));
       }
+      const int e = warp - 4 - 4 * p.splitGroups;      // epilogue warp index; warps e and e + 4 share a lane quarter
+      if (p.epiStaged && p.rowEnd && (lane & 15) == 0) {   // next tile's degrees (32 x u64 per warp = 2 lines)
+        const int64_t nrow = (tile + gridDim.x) * TC_BM + (warp & 3) * 32 + lane;
+        if (nrow < p.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rowEnd + nrow));
+      }
+      if (p.epiStaged && (p.reluOf || p.accumulate || p.omask)) {
+        // pull this warp's first chunk of the NEXT tile's epilogue operands into L2 (and, for the first
+        // tile, this one's): they stream (always cold); fetched on demand each batch exposes a DRAM latency.
+        // The epilogue paces short-K GEMMs, so the accumulator is usually ready: one tile ahead is needed.
+        const int c = n0 + (e >> 2) * 32 + (lane & 7) * 4;
+        if (c < p.outDim) {
+#pragma unroll 1
+          for (int64_t pt = (tl == 0) ? tile : tile + gridDim.x; pt <= tile + gridDim.x && pt < numTiles; pt += gridDim.x) {
+            const int64_t prow0 = pt * TC_BM + (warp & 3) * 32;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int64_t row = prow0 + i * 4 + (lane >> 3);
+              if (row < p.rows) {
+                if (p.reluOf) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.reluOf + row * p.ldR + c));
+                if (p.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.Y + row * p.ldY + c));
+                if (p.omask && (lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.omask + row * p.oldm + (c >> 5)));
+              }
+            }
+          }
+        }
+      }
       mbar_wait(&dFull[b], (tl >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmemBase + ((uint32_t)((warp & 3) * 32) << 16) + b * p.dStride;
-      const int e = warp - 4 - 4 * p.splitGroups;      // epilogue warp index; warps e and e + 4 share a lane quarter
       if (p.epiStaged) tc_epilogue_warp<EPI>(taddr, n0, row0, p, epiStg + e * EPI_STG_FLOATS, lane, myD, e >> 2, p.epiWarps >> 2);
       else if (e < 4) tc_epilogue_rows<EPI>(taddr, n0, row0 + lane, p, myD);
       tc_fence_before();
