@@ -2,15 +2,10 @@
 //
 // Replaces cublasSgemm(OP_N, OP_T) of Linear::backward_task (linear_kernel.cu:220-224):
 //     dW[o][i] += sum_v dY[v][o] * X[v][i]
-//   M = i (X columns, tiles of 128), N = o, K = v (vertices).  Both operands are
-//   MN-major in memory (X[v][i]: i contiguous; dY[v][o]: o contiguous), which tcgen05
-//   takes directly (a_major = b_major = 1): a TMA box [8 vertices][32 columns] with the
-//   128B_ATOM_32B swizzle is two canonical MN-major tf32 UMMA atoms (4 k-rows x 128 B each).
-// A CTA owns a vertex range (split-K) and up to G = 512/BN M-tiles at once, so X and
-// dY stream through HBM once; the G accumulators [128 x BN] sit side by side in TMEM.
-// Per 8-vertex step: TMA -> split warps (hi in place, lo beside) -> 3 MMAs per M-tile.
-// Partials go to a workspace [splits][out][in]; a reduce kernel adds them into dW in
-// split order (deterministic).
+//   M = i (X columns, tiles of 128), N = o, K = v (vertices).  A CTA owns a vertex range
+//   (split-K) and up to 5 M-tiles at once, so X and dY stream through HBM once; the
+//   accumulators [128 x BN] sit side by side in TMEM.  Partials go to a workspace
+//   [splits][out][in]; a reduce kernel adds them into dW in split order (deterministic).
 #include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -20,164 +15,8 @@ namespace roc {
 using namespace tc;
 
 constexpr int DW_BM = 128;
-constexpr int DW_THREADS = 256;
-constexpr int DW_MAX_STAGES = 4;
 
-struct TcDwParams {
-  float* ws;            // [splits][outDim*inDim]
-  int64_t rows;
-  int inDim, outDim;
-  int BN;               // UMMA N (outDim rounded up to 16)
-  int nbAtoms;          // 32-column atoms of dY per step
-  int G;                // M-tiles per CTA
-  int MT;               // total M-tiles
-  int64_t vPerSplit;    // vertices per split (multiple of 8)
-  uint32_t tmemCols;
-  int stages;
-  uint32_t lbo, sbo;    // descriptor strides (debug-overridable: ROC_DW_LBO / ROC_DW_SBO)
-};
-
-__global__ void __launch_bounds__(DW_THREADS, 1)
-k_tc_linear_dw(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
-               const TcDwParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int g0 = blockIdx.y * p.G;                                  // first M-tile of this CTA
-  const int nt = min(p.G, p.MT - g0);                               // M-tiles handled here
-  const uint32_t aBytes = (uint32_t)p.G * 4 * 1024;                 // G tiles x 4 atoms x 1 KB
-  const uint32_t bBytes = (uint32_t)p.nbAtoms * 1024;
-  const uint32_t stageBytes = 2 * aBytes + 2 * bBytes;
-  uint8_t* barBase = smem + (size_t)p.stages * stageBytes;
-  uint64_t* fullTma = reinterpret_cast<uint64_t*>(barBase);
-  uint64_t* fullSplit = fullTma + DW_MAX_STAGES;
-  uint64_t* empty = fullSplit + DW_MAX_STAGES;
-  uint64_t* tmemFull = empty + DW_MAX_STAGES;
-  uint32_t* tmemAddr = reinterpret_cast<uint32_t*>(tmemFull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t v0 = (int64_t)blockIdx.x * p.vPerSplit;
-  const int64_t v1 = min(p.rows, v0 + p.vPerSplit);
-  const int numSteps = (v1 > v0) ? (int)((v1 - v0 + 7) / 8) : 0;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapDY);
-    for (int s = 0; s < p.stages; s++) { mbar_init(&fullTma[s], 1); mbar_init(&fullSplit[s], 4); mbar_init(&empty[s], 1); }
-    mbar_init(tmemFull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmemAddr, p.tmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmemBase = *tmemAddr;
-
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(nt * 4 + p.nbAtoms) * 1024u;
-      for (int step = 0; step < numSteps; step++) {
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * stageBytes;
-        mbar_arrive_expect_tx(&fullTma[s], tx);
-        const int v = (int)(v0 + (int64_t)step * 8);
-        for (int a = 0; a < nt * 4; a++)
-          tma_load_2d(st + (size_t)a * 1024, &mapX, (g0 * 4 + a) * 32, v, &fullTma[s]);
-        for (int b = 0; b < p.nbAtoms; b++)
-          tma_load_2d(st + 2 * aBytes + (size_t)b * 1024, &mapDY, b * 32, v, &fullTma[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================= MMA issuer =================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(DW_BM, p.BN, 1, 1);    // both operands MN-major
-      int s = 0; uint32_t ph = 0;
-      for (int step = 0; step < numSteps; step++) {
-        mbar_wait(&fullSplit[s], ph);
-        tc_fence_after();
-        const uint32_t aHi = smem_u32(smem + (size_t)s * stageBytes);
-        const uint32_t aLo = aHi + aBytes;
-        const uint32_t bHi = aHi + 2 * aBytes;
-        const uint32_t bLo = bHi + bBytes;
-        // MN-major tf32 = SWIZZLE_128B_BASE32B: atom = 4 k-rows x 128 B (32 columns);
-        // LBO = byte stride between 32-column atoms (one 8-row TMA box = 1024),
-        // SBO = byte stride between 4-row K atoms (512)
-        const uint64_t dBh = make_sdesc(bHi, p.lbo, p.sbo, 1u), dBl = make_sdesc(bLo, p.lbo, p.sbo, 1u);
-        for (int j = 0; j < nt; j++) {
-          const uint64_t dAh = make_sdesc(aHi + j * 4096, p.lbo, p.sbo, 1u);
-          const uint64_t dAl = make_sdesc(aLo + j * 4096, p.lbo, p.sbo, 1u);
-          const uint32_t d = tmemBase + (uint32_t)(j * p.BN);
-          umma_tf32(d, dAl, dBh, idesc, step > 0 ? 1u : 0u);
-          umma_tf32(d, dAh, dBl, idesc, 1u);
-          umma_tf32(d, dAh, dBh, idesc, 1u);
-        }
-        umma_commit(&empty[s]);
-        if (step == numSteps - 1) umma_commit(tmemFull);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ========================= operand split, then epilogue =======================
-    const int t = threadIdx.x - 128;
-    int s = 0; uint32_t ph = 0;
-    const int nA4 = nt * 4 * 64;             // float4 count of the A region in use
-    const int nB4 = p.nbAtoms * 64;
-    for (int step = 0; step < numSteps; step++) {
-      mbar_wait(&fullTma[s], ph);
-      uint8_t* st = smem + (size_t)s * stageBytes;
-      float4* a = reinterpret_cast<float4*>(st);
-      float4* al = reinterpret_cast<float4*>(st + aBytes);
-      float4* b = reinterpret_cast<float4*>(st + 2 * aBytes);
-      float4* bl = reinterpret_cast<float4*>(st + 2 * aBytes + bBytes);
-      for (int i = t; i < nA4 + nB4; i += 128) {
-        float4* src = (i < nA4) ? a + i : b + (i - nA4);
-        float4* dlo = (i < nA4) ? al + i : bl + (i - nA4);
-        float4 v = *src, h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        *src = h; *dlo = l;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&fullSplit[s]);
-      if (++s == p.stages) { s = 0; ph ^= 1; }
-    }
-    // ---- epilogue: D_j[i_local][o] -> ws[split][o*inDim + i]  (lane = i_local: coalesced along i)
-    float* ws = p.ws + (size_t)blockIdx.x * ((size_t)p.inDim * p.outDim);
-    if (numSteps > 0) {
-      mbar_wait(tmemFull, 0);
-      tc_fence_after();
-    }
-    for (int j = 0; j < nt; j++) {
-      const int i = (g0 + j) * DW_BM + (warp - 4) * 32 + lane;
-      const uint32_t taddr = tmemBase + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(j * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
-        if (numSteps > 0) { tmem_ld16(taddr + (uint32_t)c0, r); tmem_ld_wait(); }
-        else {
-#pragma unroll
-          for (int k = 0; k < 16; k++) r[k] = 0u;
-        }
-        if (i < p.inDim) {
-#pragma unroll
-          for (int k = 0; k < 16; k++) {
-            const int o = c0 + k;
-            if (o < p.outDim) ws[(size_t)o * p.inDim + i] = __uint_as_float(r[k]);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
-}
-
-// ---------------------------------------------------------------------------
-// TS variant: X^T reaches the tensor core through TMEM (A operand, K-major: lane =
+// X^T reaches the tensor core through TMEM (A operand, K-major: lane =
 // X column i, TMEM column = vertex), so the X tile crosses shared memory once (TMA in,
 // one transposing read by the split warps) instead of five times.  Only the small
 // dY tile is split hi/lo in shared memory (B operand, MN-major, as above).
@@ -395,52 +234,31 @@ k_tc_splitk_reduce(int64_t count, int splits, const float* __restrict__ part, fl
   }
 }
 
-struct DwPlan { int BN, nb, G, MT, groups, splits, stages; size_t stageBytes; bool ts; };
+struct DwPlan { int BN, nb, G, MT, groups, splits, stages; size_t stageBytes; };
 
 static int tc_dw_plan(int64_t rows, int inDim, int outDim, DwPlan* q) {
   if (outDim > 256 || outDim < 1 || inDim < 4 || rows < 8) return ROC_ERR_UNSUPPORTED;
   q->BN = (outDim + 15) / 16 * 16;
   q->nb = (outDim + 31) / 32;
   q->MT = (inDim + DW_BM - 1) / DW_BM;
-  {
-    // TS plan: accumulators in <= 320 TMEM columns, 192 columns of A slots
-    const char* e = getenv("ROC_B200_GEMM");
-    int g = 320 / q->BN;
-    if (g > q->MT) g = q->MT;
-    if (g >= 1 && !(e && e[0] == 's' && e[1] == 's')) {
-      q->ts = true;
-      q->G = g;
-      q->groups = (q->MT + g - 1) / g;
-      q->stageBytes = (size_t)g * DWT_KS * DW_BM * 4 + (size_t)2 * q->nb * 1024 * (DWT_KS / 8) + 2048 /* mask box */;
-      int st = (int)((200 * 1024) / q->stageBytes);
-      if (st > DWT_MAX_STAGES) st = DWT_MAX_STAGES;
-      q->stages = st;
-      int sp = sm_count() / q->groups;
-      if (sp < 1) sp = 1;
-      int64_t maxSp = (rows + 63) / 64;
-      if (sp > maxSp) sp = (int)maxSp;
-      q->splits = sp;
-      if (st >= 2) return ROC_OK;
-    }
-    q->ts = false;
-  }
-  int g = 512 / q->BN;
+  // accumulators in <= 320 TMEM columns, 192 columns of A slots
+  { const char* e = getenv("ROC_B200_GEMM"); if (e && e[0] == 'n' && e[1] == 'o') return ROC_ERR_UNSUPPORTED; }   // "notc"
+  int g = 320 / q->BN;
   if (g > q->MT) g = q->MT;
-  // shared memory per stage: 2 * (G * 4 KB + nb KB); want >= 3 stages in ~200 KB
-  while (g > 1 && (size_t)2 * (g * 4 + q->nb) * 1024 * 3 > 200 * 1024) g--;
+  if (g < 1) return ROC_ERR_UNSUPPORTED;
   q->G = g;
   q->groups = (q->MT + g - 1) / g;
-  q->stageBytes = (size_t)2 * (g * 4 + q->nb) * 1024;
+  q->stageBytes = (size_t)g * DWT_KS * DW_BM * 4 + (size_t)2 * q->nb * 1024 * (DWT_KS / 8) + 2048 /* mask box */;
   int st = (int)((200 * 1024) / q->stageBytes);
-  if (st > DW_MAX_STAGES) st = DW_MAX_STAGES;
-  if (st < 2) return ROC_ERR_UNSUPPORTED;
+  if (st > DWT_MAX_STAGES) st = DWT_MAX_STAGES;
   q->stages = st;
   int sp = sm_count() / q->groups;
   if (sp < 1) sp = 1;
   int64_t maxSp = (rows + 63) / 64;
   if (sp > maxSp) sp = (int)maxSp;
   q->splits = sp;
-  return ROC_OK;
+  if (st >= 2) return ROC_OK;
+  return ROC_ERR_UNSUPPORTED;
 }
 
 size_t tc_dw_workspace_bytes(int64_t rows, int inDim, int outDim) {
@@ -458,7 +276,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
   const size_t count = (size_t)inDim * outDim;
   if (wsBytes < (size_t)q.splits * count * sizeof(float)) return ROC_ERR_INVALID;
   CUtensorMap mapX, mapDY;
-  if (q.ts) {
+  {
     if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, DWT_KS, DW_BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return ROC_ERR_UNSUPPORTED;
     if (!make_tmap_f32_2d(&mapDY, dY, (uint64_t)rows, (uint64_t)outDim, (uint64_t)ldDY, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
     TcDwTsParams t{};
@@ -489,31 +307,7 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     ROC_LAUNCH_CHECK();
     return ROC_OK;
   }
-  if (dm) return ROC_ERR_UNSUPPORTED;   // only the TS kernel fuses the dropout mask
-  if (!make_tmap_f32_2d(&mapX, X, (uint64_t)rows, (uint64_t)inDim, (uint64_t)ldX, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
-  if (!make_tmap_f32_2d(&mapDY, dY, (uint64_t)rows, (uint64_t)outDim, (uint64_t)ldDY, 8, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return ROC_ERR_UNSUPPORTED;
-  TcDwParams p{};
-  p.ws = workspace; p.rows = rows; p.inDim = inDim; p.outDim = outDim; p.BN = q.BN; p.nbAtoms = q.nb; p.G = q.G;
-  p.MT = q.MT; p.stages = q.stages;
-  { const char* e = getenv("ROC_DW_LBO"); p.lbo = e ? (uint32_t)atoi(e) : 1024u; e = getenv("ROC_DW_SBO"); p.sbo = e ? (uint32_t)atoi(e) : 512u; }
-  p.vPerSplit = ((rows + q.splits - 1) / q.splits + 7) / 8 * 8;
-  uint32_t cols = 32;
-  while ((int)cols < q.G * q.BN) cols <<= 1;
-  p.tmemCols = cols;
-  const size_t smemBytes = (size_t)q.stages * q.stageBytes + 1024 + 256;
-  static size_t configured = 0;
-  if (smemBytes > configured) {
-    ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    configured = smemBytes;
-  }
-  dim3 grid((unsigned)q.splits, (unsigned)q.groups, 1);
-  k_tc_linear_dw<<<grid, DW_THREADS, smemBytes, st>>>(mapX, mapDY, p);
-  ROC_LAUNCH_CHECK();
-  int64_t blocks = ((int64_t)count + 255) / 256;
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  k_tc_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>((int64_t)count, q.splits, workspace, dW);
-  ROC_LAUNCH_CHECK();
-  return ROC_OK;
+  return ROC_ERR_UNSUPPORTED;
 }
 
 }  // namespace roc

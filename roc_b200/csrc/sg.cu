@@ -296,105 +296,6 @@ sg_chunk_kernel(const SgParams p) {
   while (cur + 1 < r1) { advance(); flush(); }  // trailing zero-degree rows
 }
 
-// ------------------------------------------------- main kernel, variant S ---
-// Same schedule and results as sg_chunk_kernel, different loop shape: each
-// iteration gathers the next n = min(U, edges left in this row segment, edges
-// left in the index batch) rows and adds them without per-edge boundary tests, so
-// the row store appears once in the code (smallest instruction footprint).
-template <int VEC, int L, int NCH, int U, int MINB>
-__global__ void __launch_bounds__(SG_THREADS, MINB)
-sg_chunk_kernel_s(const SgParams p) {
-  typedef typename V<VEC>::T T;
-  constexpr int WPB = SG_THREADS / L;
-  constexpr uint32_t CH = SG_CH;
-  const int lane = threadIdx.x % L;
-  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
-  if (w >= p.numChunks) return;
-  const unsigned wmask = (L == 32) ? 0xffffffffu
-                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
-  const uint32_t* __restrict__ rs = p.rs;
-  const uint32_t* __restrict__ col = p.col;
-  const T* __restrict__ in = reinterpret_cast<const T*>(p.in) + lane;
-  bool act[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
-
-  const uint32_t cb = w * CH;
-  const uint32_t ce = min(cb + CH, p.E);
-  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
-  uint32_t cur, curS, curT, segEnd, e;
-  int kind;
-  bool carryIn = false;
-  if (r0 > 0) {
-    uint32_t pe = rs[r0], ps = rs[r0 - 1];
-    if (pe > cb && pe - ps > CH) {
-      carryIn = true;
-      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
-    }
-  }
-  if (!carryIn) {
-    if (r0 >= r1) return;
-    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
-    bool heavy = curT - curS > CH;
-    segEnd = heavy ? min(curT, ce) : curT;
-    kind = heavy ? 2 : 1;
-  }
-  T acc[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) acc[ch] = V<VEC>::zero();
-
-  uint32_t base = e;                                   // first edge of the index batch held in `idx`
-  uint32_t idx = (base + lane < p.E) ? __ldg(col + base + lane) : 0u;
-  for (;;) {
-    // ---- add the rest of this segment
-    while (e < segEnd) {
-      if (e >= base + L) {                              // refill the index batch
-        base = e;
-        idx = (base + lane < p.E) ? __ldg(col + base + lane) : 0u;
-      }
-      const uint32_t off = e - base;
-      const uint32_t n = min(min((uint32_t)U, segEnd - e), (uint32_t)L - off);
-      T v[U][NCH];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const uint32_t src = __shfl_sync(wmask, idx, off + u, L);
-        const bool ok = (uint32_t)u < n;
-        const T* rowp = in + (size_t)src * p.ldIn;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++)
-          v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++)
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
-      e += n;
-    }
-    // ---- store the segment (the only store site)
-    {
-      T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
-                           : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
-      dst += lane;
-      const int epi = (kind == 1) ? p.epi : 0;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        if (act[ch]) {
-          if (epi) epi_store<VEC>(acc[ch], dst + ch * L, curT - curS, epi);
-          else V<VEC>::st(dst + ch * L, acc[ch]);
-        }
-        acc[ch] = V<VEC>::zero();
-      }
-    }
-    // ---- next owned row, if any
-    cur += 1;
-    if (cur >= r1) break;
-    curS = curT; curT = rs[cur + 1];
-    const bool heavy = curT - curS > CH;
-    segEnd = heavy ? min(curT, ce) : curT;
-    kind = heavy ? 2 : 1;
-  }
-}
-
 // ------------------------------------------------- main kernel, variant C ---
 // Same schedule, same per-row summation order, but the gathered rows are staged in
 // shared memory with cp.async (LDGSTS) instead of registers: every lane copies its
@@ -411,138 +312,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int L, int NCH, int GROUP, int P>
-__global__ void __launch_bounds__(SG_THREADS, 3)
-sg_chunk_kernel_c(const SgParams p) {
-  typedef float4 T;
-  constexpr int WPB = SG_THREADS / L;
-  constexpr uint32_t CH = SG_CH;
-  constexpr int DEPTH = GROUP * P;
-  extern __shared__ __align__(16) float4 sg_ring[];
-  const int lane = threadIdx.x % L;
-  const uint32_t w = blockIdx.x * WPB + threadIdx.x / L;
-  // this lane's column of the worker's ring: slot s, chunk ch -> ring[(s * NCH + ch) * L]
-  float4* ring = sg_ring + (size_t)(threadIdx.x / L) * (DEPTH * NCH * L) + lane;
-  if (w >= p.numChunks) return;
-  const unsigned wmask = (L == 32) ? 0xffffffffu
-                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
-  const uint32_t* __restrict__ rs = p.rs;
-  const uint32_t* __restrict__ col = p.col;
-  const T* __restrict__ in = reinterpret_cast<const T*>(p.in) + lane;
-  bool act[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
-
-  const uint32_t cb = w * CH;
-  const uint32_t ce = min(cb + CH, p.E);
-  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
-  uint32_t cur, curS, curT, segEnd, e;
-  int kind;
-  bool carryIn = false;
-  if (r0 > 0) {
-    uint32_t pe = rs[r0], ps = rs[r0 - 1];
-    if (pe > cb && pe - ps > CH) {
-      carryIn = true;
-      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
-    }
-  }
-  if (!carryIn) {
-    if (r0 >= r1) return;
-    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
-    bool heavy = curT - curS > CH;
-    segEnd = heavy ? min(curT, ce) : curT;
-    kind = heavy ? 2 : 1;
-  }
-  uint32_t ee;
-  if (r1 > r0) {
-    uint32_t s = rs[r1 - 1], t = rs[r1];
-    ee = (t - s > CH) ? min(t, ce) : t;
-  } else {
-    ee = segEnd;
-  }
-  const uint32_t eb = e;
-  const uint32_t nE = ee - eb;
-  const uint32_t nG = (nE + GROUP - 1) / GROUP;
-
-  T acc[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  auto flush = [&]() {
-    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
-                         : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
-    dst += lane;
-    const int epi = (kind == 1) ? p.epi : 0;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ch++) {
-      if (act[ch]) {
-        if (epi) epi_store<4>(acc[ch], dst + ch * L, curT - curS, epi);
-        else *(dst + ch * L) = acc[ch];
-      }
-      acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto advance = [&]() {
-    cur += 1; curS = curT; curT = rs[cur + 1];
-    bool heavy = curT - curS > CH;
-    segEnd = heavy ? min(curT, ce) : curT;
-    kind = heavy ? 2 : 1;
-  };
-
-  // issue side: L source ids per batch (one per lane), next batch prefetched
-  uint32_t idx = (eb + lane < ee) ? __ldg(col + eb + lane) : 0u;
-  uint32_t nextIdx = (eb + L + lane < ee) ? __ldg(col + eb + L + lane) : 0u;
-  auto issue = [&](uint32_t gi) {
-    if (gi < nG) {
-      const uint32_t off = gi * GROUP;          // edge offset from eb (groups never straddle a batch: GROUP | L)
-      const uint32_t inb = off & (uint32_t)(L - 1);
-      if (inb == 0 && off > 0) {
-        idx = nextIdx;
-        const uint32_t nk = eb + off + L + lane;
-        nextIdx = (nk < ee) ? __ldg(col + nk) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < GROUP; u++) {
-        const uint32_t k = off + u;
-        if (k < nE) {
-          const uint32_t src = __shfl_sync(wmask, idx, inb + u, L);
-          const T* rowp = in + (size_t)src * p.ldIn;
-          float4* slot = ring + (size_t)(k % DEPTH) * (NCH * L);
-#pragma unroll
-          for (int ch = 0; ch < NCH; ch++)
-            if (act[ch]) cp_async16(slot + ch * L, rowp + ch * L);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int g = 0; g < P; g++) issue((uint32_t)g);
-#pragma unroll 1
-  for (uint32_t g = 0; g < nG; g++) {
-    cp_async_wait<P - 1>();          // group g has landed (at most P-1 younger groups still in flight)
-#pragma unroll
-    for (int u = 0; u < GROUP; u++) {
-      const uint32_t k = g * GROUP + u;
-      if (k < nE) {
-        const uint32_t ecur = eb + k;
-        while (ecur == segEnd) { flush(); advance(); }
-        const float4* slot = ring + (size_t)(k % DEPTH) * (NCH * L);
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) {
-          if (act[ch]) {
-            const float4 v = slot[ch * L];
-            acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
-          }
-        }
-      }
-    }
-    issue(g + P);                    // refills exactly the slots consumed above
-  }
-  flush();
-  while (cur + 1 < r1) { advance(); flush(); }
-}
 
 // ------------------------------------------- main kernel, variant C (lean) ---
 // Variant C with the instruction stream trimmed (r1 run 10: the first version issued
@@ -817,13 +586,12 @@ sg_fixup_big_kernel(const SgParams p) {
   }
 }
 
-// Loop shape: A (per-edge row test, gathers overlap across short rows) wins on
-// sparse graphs with narrow rows, S (one store site) on wide rows and on dense
-// graphs where almost every row spans chunks (r1 run 3: R-MAT-22 H=16 1.42 vs 2.05 ms,
-// H=256 10.9 vs 9.9 ms; Reddit-shaped H=64 3.68 vs 3.18 ms).  ROC_SG_VARIANT=a|s forces one.
+// Variant A keeps the gathers in registers, variant C stages them in shared memory with
+// cp.async; C wins once a row needs two or more float4 per lane at L = 32 (H > 128).
+// ROC_SG_VARIANT=a|c forces one (experiments / cross-checks).
 static int sg_variant_env() {
   static int v = -2;
-  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'a' ? 0 : (e[0] == 'c' ? 2 : 1)); }
+  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'c' ? 2 : 0); }
   return v;
 }
 static int sg_deep_env() {   // ROC_SG_DEEP=1: variant C with a 2x deeper ring (experiments)
@@ -876,8 +644,7 @@ static int launch_cfg(const SgParams& p, cudaStream_t st) {
       }
     }
     if (!done) {
-      if (variant == 0) sg_chunk_kernel<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
-      else sg_chunk_kernel_s<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
+      sg_chunk_kernel<VEC, L, NCH, U, MINB><<<grid, SG_THREADS, 0, st>>>(p);
       ROC_LAUNCH_CHECK();
     }
   }
