@@ -121,7 +121,9 @@ template <> struct V<4> {
     return make_float4(div1(a.x, d), div1(a.y, d), div1(a.z, d), div1(a.w, d));
   }
   static __device__ __forceinline__ T rdiv(const T& a, const RowDiv& r) {
-    return make_float4(rowdiv(a.x, r), rowdiv(a.y, r), rowdiv(a.z, r), rowdiv(a.w, r));
+    float v[4] = {a.x, a.y, a.z, a.w};
+    rowdiv4(v, r);          // one safety test for the four quotients
+    return make_float4(v[0], v[1], v[2], v[3]);
   }
   static __device__ __forceinline__ T relu(const T& a) {
     return make_float4(relu_nanprop(a.x), relu_nanprop(a.y), relu_nanprop(a.z), relu_nanprop(a.w));
@@ -259,20 +261,31 @@ sg_chunk_kernel(const SgParams p) {
   // Every lane reads the source ids itself (same address across the worker: one broadcast
   // transaction from L1); sub-warp shuffles with a runtime mask cost a MATCH.ANY sequence each.
   (void)wmask;
+  // Gathers are unpredicated: a group that runs past the worker's last edge re-reads that edge's
+  // source (index clamped; an L1 hit) and the tail values are simply never added.  With the tail
+  // predicates (16 ISETP + 20 zero-inits per group) and a 64 x 64-bit address multiply the group
+  // preamble was 146 SASS instructions for 8 gathers (r1 run 39); now one VIMNMX + LDG + IMAD.WIDE
+  // + LDG.128 per edge.
+  // lanes beyond the row's last column gather that last column instead (same sector, no extra
+  // traffic): their sums are never stored (flush tests act[]), and no load needs a predicate
+  const char* inl[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++)
+    inl[ch] = reinterpret_cast<const char*>(in + min((uint32_t)(lane + ch * L), p.Q - 1u));
+  const uint32_t rowBytes = (uint32_t)p.ldIn * (uint32_t)sizeof(T);
+  const uint32_t eLast = ee - 1u;
 #pragma unroll 1
   for (uint32_t base = e; base < ee; base += U) {
     const uint32_t cnt = min((uint32_t)U, ee - base);
     uint32_t srcs[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) srcs[u] = ((uint32_t)u < cnt) ? __ldg(col + base + u) : 0u;
+    for (int u = 0; u < U; u++) srcs[u] = __ldg(col + min(base + (uint32_t)u, eLast));
     T v[U][NCH];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const bool ok = (uint32_t)u < cnt;
-      const T* rowp = in + (size_t)srcs[u] * p.ldIn + lane;
+      const uint64_t off = (uint64_t)srcs[u] * rowBytes;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ch++)
-        v[u][ch] = (ok && act[ch]) ? V<VEC>::ld(rowp + ch * L) : V<VEC>::zero();
+      for (int ch = 0; ch < NCH; ch++) v[u][ch] = V<VEC>::ld(reinterpret_cast<const T*>(inl[ch] + off));
     }
     if (segEnd - base >= (uint32_t)U) {
       // all U edges belong to the current row segment: no boundary tests
@@ -281,14 +294,24 @@ sg_chunk_kernel(const SgParams p) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
     } else {
+      // a row ends inside this group: one rolled loop over the row segments of the group (predicated
+      // adds of the edges [pos, lim) of the current segment, then ONE copy of the row store).  The
+      // unrolled per-edge `while (edge == segEnd) { flush; advance; }` had 8 inlined copies of the
+      // store and cost ~180 SASS instructions per row (42 % of all instructions, r1 run 39).
+      uint32_t pos = 0;
+      for (;;) {
+        const uint32_t lim = min(cnt, segEnd - base);
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        if ((uint32_t)u < cnt) {
-          const uint32_t ecur = base + u;
-          while (ecur == segEnd) { flush(); advance(); }
+        for (int u = 0; u < U; u++) {
+          if ((uint32_t)u >= pos && (uint32_t)u < lim) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+            for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
+          }
         }
+        pos = lim;
+        if (pos >= cnt) break;
+        flush();
+        advance();
       }
     }
   }
