@@ -373,11 +373,12 @@ k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t 
     const int mk = mask[r];
     const int tl = ONEHOT ? -1 : labelIdx[r];
     float best = 0.0f; int bestIdx = -1; int trueIdx = -1; float pTrue = 0.f;
+    const RowDiv rsum = rowdiv_make(sum);      // p = v / sum, bit-identical to the IEEE divide (common.cuh)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int c = lr + j * LR;
       if (c < C) {
-        const float p = v[j] / sum;
+        const float p = rowdiv(v[j], rsum);
         if (p > best) { best = p; bestIdx = c; }
         float lab;
         if (ONEHOT) { lab = onehot[r * ldl + c]; if (lab > 0.5f) trueIdx = c; }

@@ -278,8 +278,14 @@ sg_chunk_kernel(const SgParams p) {
   for (uint32_t base = e; base < ee; base += U) {
     const uint32_t cnt = min((uint32_t)U, ee - base);
     uint32_t srcs[U];
+    if (cnt == (uint32_t)U) {
+      const uint32_t* colp = col + base;       // full group: one address, immediate offsets
 #pragma unroll
-    for (int u = 0; u < U; u++) srcs[u] = __ldg(col + min(base + (uint32_t)u, eLast));
+      for (int u = 0; u < U; u++) srcs[u] = __ldg(colp + u);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++) srcs[u] = __ldg(col + min(base + (uint32_t)u, eLast));
+    }
     T v[U][NCH];
 #pragma unroll
     for (int u = 0; u < U; u++) {
