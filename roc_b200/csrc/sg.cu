@@ -238,9 +238,10 @@ sg_chunk_kernel(const SgParams p) {
   // inlining it at every edge position made the kernel 4096 SASS instructions and
   // instruction-fetch bound (ncu: stalled_no_instruction 22.9 per issue, r1 run 2).
   auto flush = [&]() {
-    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
-                         : out + (size_t)cur * p.ldOut;
-    dst += lane;
+    char* dstb = (kind == 0)
+        ? reinterpret_cast<char*>(reinterpret_cast<T*>(p.carry) + lane) + (uint64_t)p.carryIdx[w] * ((uint32_t)p.ldC * (uint32_t)sizeof(T))
+        : reinterpret_cast<char*>(out + lane) + (uint64_t)cur * ((uint32_t)p.ldOut * (uint32_t)sizeof(T));
+    T* dst = reinterpret_cast<T*>(dstb);
     const int epi = (kind == 1) ? p.epi : 0;
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
@@ -293,15 +294,11 @@ sg_chunk_kernel(const SgParams p) {
 #pragma unroll
       for (int ch = 0; ch < NCH; ch++) v[u][ch] = V<VEC>::ld(reinterpret_cast<const T*>(inl[ch] + off));
     }
-    if (segEnd - base >= (uint32_t)U) {
-      // all U edges belong to the current row segment: no boundary tests
-#pragma unroll
-      for (int u = 0; u < U; u++)
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) V<VEC>::add(acc[ch], v[u][ch]);
-    } else {
-      // a row ends inside this group: one rolled loop over the row segments of the group (predicated
-      // adds of the edges [pos, lim) of the current segment, then ONE copy of the row store).  The
+    {
+      // One rolled loop over the row segments of the group (predicated adds of the edges [pos, lim)
+      // of the current segment, then ONE copy of the row store).  A separate branch-free path for
+      // groups inside one row did not pay: the two 16-lane workers of a warp rarely agree, so the
+      // warp ran both paths in most iterations (r1 run 45).  The
       // unrolled per-edge `while (edge == segEnd) { flush; advance; }` had 8 inlined copies of the
       // store and cost ~180 SASS instructions per row (42 % of all instructions, r1 run 39).
       uint32_t pos = 0;
