@@ -374,29 +374,50 @@ k_softmax_xent_narrow(int64_t rows, int C, const float* __restrict__ z, int64_t 
     const int tl = ONEHOT ? -1 : labelIdx[r];
     float best = 0.0f; int bestIdx = -1; int trueIdx = -1; float pTrue = 0.f;
     const RowDiv rsum = rowdiv_make(sum);      // p = v / sum, bit-identical to the IEEE divide (common.cuh)
+    float pv[4] = {v[0], v[1], v[2], v[3]};    // columns beyond C hold 0 (a safe numerator)
+    rowdiv4(pv, rsum);
+    float gvv[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int c = lr + j * LR;
+      gvv[j] = 0.f;
       if (c < C) {
-        const float p = rowdiv(v[j], rsum);
+        const float p = pv[j];
         if (p > best) { best = p; bestIdx = c; }
         float lab;
         if (ONEHOT) { lab = onehot[r * ldl + c]; if (lab > 0.5f) trueIdx = c; }
         else { lab = (c == tl) ? 1.0f : 0.0f; if (c == tl) trueIdx = c; }
         if (trueIdx == c) pTrue = p;
-        float gv = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
-        if (rowEnd) gv = rowdiv(gv, rd);   // fused InDegreeNorm backward (== gv / sqrtf(deg))
-        g[r * ldg + c] = gv;
+        gvv[j] = (mk == ROC_MASK_TRAIN) ? p - lab : 0.0f;
       }
     }
+    if (rowEnd) rowdiv4(gvv, rd);             // fused InDegreeNorm backward (== gv / sqrtf(deg))
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = lr + j * LR;
+      if (c < C) g[r * ldg + c] = gvv[j];
+    }
+    // argmax with calc_loss's rule (larger p wins, ties -> smaller index; bestIdx stays -1 when no
+    // p > 0): max-reduce of the key (p bits, ~index) — p >= 0, so its bit pattern orders like the value
+    unsigned long long key = (bestIdx < 0) ? 0ull
+        : (((unsigned long long)__float_as_uint(best)) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bestIdx);
 #pragma unroll
     for (int o = LR / 2; o > 0; o >>= 1) {
-      float ob = __shfl_xor_sync(gmask, best, o, LR);
-      int oi = __shfl_xor_sync(gmask, bestIdx, o, LR);
-      if (ob > best || (ob == best && oi >= 0 && (bestIdx < 0 || oi < bestIdx))) { best = ob; bestIdx = oi; }
-      int ot = __shfl_xor_sync(gmask, trueIdx, o, LR);
-      float op = __shfl_xor_sync(gmask, pTrue, o, LR);
-      if (ot > trueIdx) { trueIdx = ot; pTrue = op; }
+      const unsigned long long ok = __shfl_xor_sync(gmask, key, o, LR);
+      key = (ok > key) ? ok : key;
+      if (ONEHOT) {
+        int ot = __shfl_xor_sync(gmask, trueIdx, o, LR);
+        float op = __shfl_xor_sync(gmask, pTrue, o, LR);
+        if (ot > trueIdx) { trueIdx = ot; pTrue = op; }
+      }
+    }
+    bestIdx = (key == 0ull) ? -1 : (int)(0xFFFFFFFFu - (uint32_t)key);
+    if (!ONEHOT) {
+      // the class index is known: its probability lives in lane (tl % LR) of this row's group
+      const int owner = ((threadIdx.x & 31) / LR) * LR + ((tl >= 0 && tl < C) ? tl % LR : 0);
+      const float fromOwner = __shfl_sync(gmask, pTrue, owner, 32);
+      trueIdx = (tl >= 0 && tl < C) ? tl : -1;
+      pTrue = (trueIdx >= 0) ? fromOwner : 0.f;
     }
     if (lr == 0) {
       const bool ok = (trueIdx == bestIdx);
