@@ -316,7 +316,9 @@ def test_linear_bwd_fused_epilogue_matches_separate_kernels_bitwise(n, i, o, rat
     first, seed, step = 0, (1 << 32) | 7, 3
     x = K.padded(n, i, DEV, fill=torch.from_numpy(np.maximum(r.randn(n, i), 0).astype(np.float32)).to(DEV))  # a relu output
     w = torch.from_numpy((r.randn(o, i) * 0.1).astype(np.float32)).to(DEV)
-    dy = torch.from_numpy(r.randn(n, o).astype(np.float32)).to(DEV)
+    dy_np = r.randn(n, o).astype(np.float32)
+    dy_np[r.rand(n) < 0.6] = 0.0          # rows outside the training mask carry no gradient (zero-row fast path)
+    dy = torch.from_numpy(dy_np).to(DEV)
     mask = K.dropout_mask(n, i, first, rate, seed, step, DEV) if rate > 0 else None
     # separate: linear bwd (+dropout bwd) -> indegree_norm with relu mask
     g0 = K.padded(n, o, DEV, fill=dy)
