@@ -34,7 +34,7 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   colLeft = ebounds[2 * myPart]; colRight = ebounds[2 * myPart + 1];
   const size_t nloc = (size_t)rowRight - rowLeft + 1;
   const size_t eloc = (size_t)(colRight + 1 - colLeft);
-  if (rt->numParts > 1 || true)
+  if (rt->numParts > 1)
     fprintf(stderr, "[roc_b200] part %d/%d: rows [%u, %u] edges [%zu, %zu]\n", myPart, numParts, rowLeft,
             rowRight, (size_t)colLeft, (size_t)colRight);
   // raw slices -> device, then the device CSR build (init_graph_kernel's job)
