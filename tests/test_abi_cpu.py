@@ -35,6 +35,25 @@ def test_no_undeclared_prototypes():
     assert set(_lib.PROTOTYPES) <= names
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the C structs (roc_linear_bwd_args, roc_perf_metrics) have the C layout:
+    a tiny C program compiled against include/roc_b200.h prints sizeof / offsetof of every field."""
+    fields = [f for f, _ in _lib.LinearBwdArgs._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "roc_b200.h"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(roc_linear_bwd_args));']
+    prog += ['  printf("%%zu\\n", offsetof(roc_linear_bwd_args, %s));' % f for f in fields]
+    prog += ['  printf("%zu\\n", sizeof(roc_perf_metrics));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == C.sizeof(_lib.LinearBwdArgs)
+    for f, off in zip(fields, out[1:1 + len(fields)]):
+        assert getattr(_lib.LinearBwdArgs, f).offset == off, f
+    assert out[-1] == C.sizeof(_lib.PerfMetrics)
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
