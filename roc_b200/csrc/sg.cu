@@ -28,8 +28,10 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace roc {
 
@@ -48,6 +50,7 @@ struct roc_sg_plan {
   const uint32_t* col = nullptr;  // caller's colSrc
   float* carry = nullptr;         // [numCarries][carryLd]
   size_t carryLd = 0;
+  uint64_t inRows = 1;            // 1 + largest source id in col: the rows a TMA tensor map of the input spans
   int device = 0;
 };
 
@@ -511,6 +514,232 @@ sg_chunk_kernel_c2(const SgParams p) {
   while (cur + 1 < r1) { advance(); flush(); }
 }
 
+// ------------------------------------------------- main kernel, variant T ---
+// Same schedule and the same per-row summation order again, but the neighbour rows are fetched by
+// the TMA unit: one `cp.async.bulk.tensor ... tile::gather4` per four edges (four row indices in
+// one instruction, sm_100 only) lands 4 x rowBytes in the worker's shared-memory ring and
+// completes on an mbarrier; the lanes then add with LDS.128 + FADD.  What this buys over the
+// register variant A: (1) bytes in flight are bounded by the ring (P stages x S gather4s per
+// worker, ~100 KB per SM) instead of by the register file — variant A holds 8 rows per lane in
+// registers, issues them as a burst, waits for all of them and only then adds, so its *average*
+// bytes in flight are well under half of its peak (ncu r1 run 45: latency-bound at 0.52 of the
+// DRAM peak, 47 % issue utilisation, nothing saturated); the ring is refilled stage by stage,
+// so it stays full.  (2) one TMA instruction per 4 edges replaces 4 x (index load + IMAD.WIDE +
+// LDG.128) per lane group.  MODE 1 issues one plain `cp.async.bulk` per row instead (no tensor
+// map; kept for measurement).
+// The tensor map's box is L*NCH*4 floats wide (the worker's whole lane span) over a tensor
+// that is Q*4 floats wide: columns past the row's end are zero-filled by the TMA unit, which
+// makes the shared-memory row pitch a compile-time constant and the adds unpredicated.
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SG_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SG_DONE;\n\t"
+      "bra SG_WAIT;\n\t"
+      "SG_DONE:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* m, int c0, uint32_t r0, uint32_t r1,
+                                            uint32_t r2, uint32_t r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int L, int NCH, int S, int P, int NT, int MINB, int MODE>
+__global__ void __launch_bounds__(NT, MINB)
+sg_chunk_kernel_t(const SgParams p, const __grid_constant__ CUtensorMap tmap) {
+  typedef float4 T;
+  constexpr int WPB = NT / L;
+  constexpr uint32_t CH = SG_CH;
+  constexpr int G = 4 * S;                       // edges per stage
+  constexpr uint32_t SLOTB = NCH * L * 16;       // shared-memory bytes per gathered row
+  constexpr uint32_t G4B = 4 * SLOTB;            // one gather4
+  constexpr uint32_t STAGEB = S * G4B;
+  constexpr uint32_t RINGB = P * STAGEB;
+  extern __shared__ __align__(128) unsigned char sg_smem_t[];
+  const int lane = threadIdx.x % L;
+  const int wi = threadIdx.x / L;
+  const uint32_t w = blockIdx.x * WPB + wi;
+  if (w >= p.numChunks) return;
+  const unsigned wmask = (L == 32) ? 0xffffffffu
+                                   : (((1u << L) - 1u) << (((threadIdx.x & 31) / L) * L));
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(sg_smem_t);
+  const uint32_t ring = smem0 + wi * RINGB;
+  const uint32_t bars = smem0 + WPB * RINGB + wi * (P * 8);
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t* __restrict__ col = p.col;
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * L) < p.Q;
+
+  const uint32_t cb = w * CH;
+  const uint32_t ce = min(cb + CH, p.E);
+  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
+  uint32_t cur, curS, curT, segEnd, e;
+  int kind;
+  bool carryIn = false;
+  if (r0 > 0) {
+    uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true;
+      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) return;
+    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  }
+  uint32_t ee;
+  if (r1 > r0) {
+    uint32_t s = rs[r1 - 1], t = rs[r1];
+    ee = (t - s > CH) ? min(t, ce) : t;
+  } else {
+    ee = segEnd;
+  }
+  const uint32_t eb = e;
+  const uint32_t nE = ee - eb;
+  const uint32_t nStages = (nE + G - 1) / G;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < P; s++) mbar_init_a(bars + 8 * s, 1);
+    tc::fence_barrier_init();
+  }
+  __syncwarp(wmask);
+
+  T acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&]() {
+    T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)p.carryIdx[w] * p.ldC
+                         : reinterpret_cast<T*>(p.out) + (size_t)cur * p.ldOut;
+    dst += lane;
+    const int epi = (kind == 1) ? p.epi : 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      if (act[ch]) {
+        if (epi) epi_store<4>(acc[ch], dst + ch * L, curT - curS, epi);
+        else *(dst + ch * L) = acc[ch];
+      }
+      acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto advance = [&]() {
+    cur += 1; curS = curT; curT = rs[cur + 1];
+    bool heavy = curT - curS > CH;
+    segEnd = heavy ? min(curT, ce) : curT;
+    kind = heavy ? 2 : 1;
+  };
+
+  // stage k -> ring slot `slot`: issued by the worker's first lane.  A stage that runs past the
+  // worker's last edge repeats that edge's source (a duplicate row, L2-resident; never added).
+  const char* inB = reinterpret_cast<const char*>(p.in);
+  const uint32_t strideB = (uint32_t)p.ldIn * 16u;
+  const uint32_t rowB = p.Q * 16u;
+  auto issue = [&](uint32_t k, uint32_t slot) {
+    if (k < nStages && lane == 0) {
+      const uint32_t off = k * G;
+      const uint32_t* cp = col + eb + off;
+      const uint32_t bar = bars + slot * 8;
+      const uint32_t dst = ring + slot * STAGEB;
+      const uint32_t nv = min((uint32_t)G, nE - off);
+      if (MODE == 0) {
+        const uint32_t n4 = (nv + 3u) >> 2;
+        mbar_expect_tx_a(bar, n4 * G4B);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+          if ((uint32_t)s < n4) {
+            uint32_t i0, i1, i2, i3;
+            if ((uint32_t)(4 * s + 4) <= nv) {
+              i0 = __ldg(cp + 4 * s); i1 = __ldg(cp + 4 * s + 1); i2 = __ldg(cp + 4 * s + 2); i3 = __ldg(cp + 4 * s + 3);
+            } else {
+              const uint32_t last = nv - 1u;
+              i0 = __ldg(cp + min((uint32_t)(4 * s), last)); i1 = __ldg(cp + min((uint32_t)(4 * s + 1), last));
+              i2 = __ldg(cp + min((uint32_t)(4 * s + 2), last)); i3 = __ldg(cp + min((uint32_t)(4 * s + 3), last));
+            }
+            tma_gather4(dst + s * G4B, &tmap, 0, i0, i1, i2, i3, bar);
+          }
+        }
+      } else {
+        mbar_expect_tx_a(bar, nv * rowB);
+#pragma unroll
+        for (int u = 0; u < G; u++) {
+          if ((uint32_t)u < nv) {
+            const uint32_t src = __ldg(cp + u);
+            bulk_row(dst + u * SLOTB, inB + (size_t)src * strideB, rowB, bar);
+          }
+        }
+      }
+    }
+  };
+#pragma unroll 1
+  for (uint32_t k = 0; k < (uint32_t)P; k++) issue(k, k);
+  uint32_t slot = 0, parity = 0;
+#pragma unroll 1
+  for (uint32_t k = 0; k < nStages; k++) {
+    mbar_wait_a(bars + slot * 8, parity);
+    const uint32_t e0 = eb + k * G;
+    const uint32_t sa = ring + slot * STAGEB + lane * 16;
+    if (segEnd - e0 >= (uint32_t)G) {
+      // the whole stage lies inside the current row segment
+#pragma unroll
+      for (int u = 0; u < G; u++)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+          const float4 v = lds128(sa + u * SLOTB + ch * L * 16);
+          acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
+        }
+    } else {
+      // one rolled loop over the row segments of the stage, ONE row-store site
+      const uint32_t cnt = min((uint32_t)G, ee - e0);
+      uint32_t pos = 0;
+      for (;;) {
+        const uint32_t lim = min(cnt, segEnd - e0);
+#pragma unroll
+        for (int u = 0; u < G; u++) {
+          if ((uint32_t)u >= pos && (uint32_t)u < lim) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+              const float4 v = lds128(sa + u * SLOTB + ch * L * 16);
+              acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
+            }
+          }
+        }
+        pos = lim;
+        if (pos >= cnt) break;
+        flush();
+        advance();
+      }
+    }
+    __syncwarp(wmask);          // every lane has read the slot before the TMA unit rewrites it
+    issue(k + P, slot);
+    slot += 1;
+    if (slot == (uint32_t)P) { slot = 0; parity ^= 1u; }
+  }
+  flush();
+  while (cur + 1 < r1) { advance(); flush(); }
+}
+
 // ----------------------------------------------------------- fix-up kernel ---
 // One worker per heavy row: out[R] = epilogue(out[R] + sum_k carry[slot0 + k]), k ascending.
 template <int VEC, int L, int NCH, int U>
@@ -615,29 +844,78 @@ sg_fixup_big_kernel(const SgParams p) {
 // Variant A keeps the gathers in registers, variant C stages them in shared memory with
 // cp.async; C wins once a row needs two or more float4 per lane at L = 32 (H > 128).
 // ROC_SG_VARIANT=a|c forces one (experiments / cross-checks).
-static int sg_variant_env() {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("ROC_SG_VARIANT"); v = !e ? -1 : (e[0] == 'c' ? 2 : 0); }
-  return v;
+static int sg_variant_env() {   // -1 default, 0 = A, 2 = C, 3 = T (TMA gather4), 4 = T with per-row bulk copies
+  const char* e = getenv("ROC_SG_VARIANT");   // re-read per call: the kernel bench switches it in-process
+  if (!e) return -1;
+  switch (e[0]) { case 'a': return 0; case 'c': return 2; case 't': return 3; case 'b': return 4; default: return -1; }
 }
 static int sg_deep_env() {   // ROC_SG_DEEP=1: variant C with a 2x deeper ring (experiments)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ROC_SG_DEEP"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
+  const char* e = getenv("ROC_SG_DEEP");
+  return (e && e[0] == '1') ? 1 : 0;
+}
+static int sg_tcfg_env() {   // ROC_SG_TCFG=<n>: ring shape of variant T (experiments; see launch_t_cfg)
+  const char* e = getenv("ROC_SG_TCFG");
+  return e ? atoi(e) : -1;
 }
 
 template <int L, int NCH, int GROUP, int P>
 static cudaError_t launch_c(const SgParams& p, unsigned grid, cudaStream_t st) {
   constexpr int WPB = SG_THREADS / L;
   constexpr size_t smem = (size_t)WPB * GROUP * P * NCH * L * sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sg_chunk_kernel_c2<L, NCH, GROUP, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};      // one bit per device: the attribute is per device
+  cudaError_t e = once_per_device(configured, [] {
+    return cudaFuncSetAttribute(sg_chunk_kernel_c2<L, NCH, GROUP, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (e != cudaSuccess) return e;
   sg_chunk_kernel_c2<L, NCH, GROUP, P><<<grid, SG_THREADS, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+// ---- variant T launchers: ring = P stages x S gather4s per worker, NT threads per CTA
+template <int L, int NCH, int S, int P, int NT, int MINB, int MODE>
+static cudaError_t launch_t(const SgParams& p, const CUtensorMap& tm, cudaStream_t st) {
+  constexpr int WPB = NT / L;
+  constexpr size_t smem = (size_t)WPB * P * S * 4 * NCH * L * 16 + (size_t)WPB * P * 8;
+  static_assert(smem <= 227 * 1024, "ring too large");
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = once_per_device(configured, [] {
+    return cudaFuncSetAttribute(sg_chunk_kernel_t<L, NCH, S, P, NT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (p.numChunks + WPB - 1) / WPB;
+  sg_chunk_kernel_t<L, NCH, S, P, NT, MINB, MODE><<<grid, NT, smem, st>>>(p, tm);
+  return cudaGetLastError();
+}
+
+// Ring shapes.  cfg < 0: the default for this width (chosen by measurement).
+template <int L, int NCH, int MODE>
+static cudaError_t launch_t_cfg(const SgParams& p, const CUtensorMap& tm, int cfg, cudaStream_t st) {
+  // bytes per row slot = NCH*L*16; per worker ring = P*S*4 slots
+  if constexpr (NCH * L <= 16) {          // rows <= 256 B: 2+ workers per warp
+    switch (cfg) {
+      case 1: return launch_t<L, NCH, 2, 2, 128, 4, MODE>(p, tm, st);
+      case 2: return launch_t<L, NCH, 1, 8, 128, 3, MODE>(p, tm, st);
+      case 3: return launch_t<L, NCH, 2, 4, 128, 3, MODE>(p, tm, st);
+      case 4: return launch_t<L, NCH, 1, 4, 256, 3, MODE>(p, tm, st);
+      case 5: return launch_t<L, NCH, 1, 3, 128, 8, MODE>(p, tm, st);
+      case 6: return launch_t<L, NCH, 1, 6, 128, 4, MODE>(p, tm, st);
+      default: return launch_t<L, NCH, 1, 4, 128, 6, MODE>(p, tm, st);
+    }
+  } else if constexpr (NCH == 1) {        // 512 B rows, one worker per warp
+    switch (cfg) {
+      case 1: return launch_t<L, NCH, 2, 2, 128, 4, MODE>(p, tm, st);
+      case 2: return launch_t<L, NCH, 1, 8, 128, 3, MODE>(p, tm, st);
+      case 3: return launch_t<L, NCH, 1, 3, 128, 8, MODE>(p, tm, st);
+      default: return launch_t<L, NCH, 1, 4, 128, 6, MODE>(p, tm, st);
+    }
+  } else {                                 // 1 KB rows
+    switch (cfg) {
+      case 1: return launch_t<L, NCH, 1, 2, 128, 6, MODE>(p, tm, st);
+      case 2: return launch_t<L, NCH, 1, 6, 128, 2, MODE>(p, tm, st);
+      case 3: return launch_t<L, NCH, 1, 3, 128, 4, MODE>(p, tm, st);
+      default: return launch_t<L, NCH, 1, 4, 128, 3, MODE>(p, tm, st);
+    }
+  }
 }
 
 // variant C rings: DEPTH = GROUP * P row slots per worker, 64 KB per CTA (128 KB with ROC_SG_DEEP=1)
@@ -650,19 +928,30 @@ static cudaError_t launch_c_cfg(const SgParams& p, unsigned grid, cudaStream_t s
   else return deep ? launch_c<L, NCH, 1, 4>(p, grid, st) : launch_c<L, NCH, 1, 2>(p, grid, st);
 }
 
+struct SgLaunch {
+  int variant;               // 0 = A, 2 = C, 3 = T (gather4), 4 = T (bulk rows)
+  int tcfg;                  // ring shape of variant T (-1 = default)
+  const CUtensorMap* tmap;   // variant T (gather4) only
+};
+
 template <int VEC, int L, int NCH, int U, int MINB>
-static int launch_cfg(const SgParams& p, cudaStream_t st) {
+static int launch_cfg(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
   constexpr int WPB = SG_THREADS / L;
   if (p.numChunks) {
     unsigned grid = (p.numChunks + WPB - 1) / WPB;
-    int variant = sg_variant_env();
-    // default: rows wider than 128 floats (NCH >= 2) stage through shared memory (variant C),
-    // everything else uses the register variant A (R-MAT-22, r1 run 13, A vs C in ms:
-    // H=16 1.33/1.58, H=41 2.41/3.09, H=64 2.39/2.95, H=128 4.03/4.59, H=256 8.25/7.47)
-    if (variant < 0) variant = (NCH >= 2 && VEC == 4) ? 2 : 0;
+    int variant = how.variant;
     bool done = false;
+    if constexpr (VEC == 4 && NCH <= 2) {
+      if (variant == 3 || variant == 4) {
+        cudaError_t e = (variant == 3) ? launch_t_cfg<L, NCH, 0>(p, *how.tmap, how.tcfg, st)
+                                       : launch_t_cfg<L, NCH, 1>(p, *how.tmap, how.tcfg, st);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        done = true;
+      }
+    }
     if constexpr (VEC == 4) {
-      if (variant == 2) {
+      if (!done && variant == 2) {
         cudaError_t e = launch_c_cfg<L, NCH>(p, grid, st);
         if (e != cudaSuccess) return (int)e;
         count_launch();
@@ -687,16 +976,26 @@ static int launch_cfg(const SgParams& p, cudaStream_t st) {
 }
 
 template <int VEC>
-static int dispatch(const SgParams& p, cudaStream_t st) {
+static int dispatch(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
   const uint32_t Q = p.Q;
-  if (Q <= 4) return launch_cfg<VEC, 4, 1, 4, 4>(p, st);
-  if (Q <= 8) return launch_cfg<VEC, 8, 1, 8, 4>(p, st);
-  if (Q <= 16) return launch_cfg<VEC, 16, 1, 8, 4>(p, st);
-  if (Q <= 32) return launch_cfg<VEC, 32, 1, 8, 4>(p, st);
-  if (Q <= 64) return launch_cfg<VEC, 32, 2, 4, 3>(p, st);
-  if (Q <= 128) return launch_cfg<VEC, 32, 4, 2, 3>(p, st);
-  if (Q <= 256) return launch_cfg<VEC, 32, 8, 1, 2>(p, st);
+  if (Q <= 4) return launch_cfg<VEC, 4, 1, 4, 4>(p, how, st);
+  if (Q <= 8) return launch_cfg<VEC, 8, 1, 8, 4>(p, how, st);
+  if (Q <= 16) return launch_cfg<VEC, 16, 1, 8, 4>(p, how, st);
+  if (Q <= 32) return launch_cfg<VEC, 32, 1, 8, 4>(p, how, st);
+  if (Q <= 64) return launch_cfg<VEC, 32, 2, 4, 3>(p, how, st);
+  if (Q <= 128) return launch_cfg<VEC, 32, 4, 2, 3>(p, how, st);
+  if (Q <= 256) return launch_cfg<VEC, 32, 8, 1, 2>(p, how, st);
   return ROC_ERR_UNSUPPORTED;
+}
+
+// The variant for a vectorised launch of Q float4 columns.  Default: chosen by measurement per width
+// (DESIGN.md §3.1); ROC_SG_VARIANT=a|c|t|b forces one (experiments / cross-checks).
+static int pick_variant(uint32_t Q, bool vec) {
+  int v = sg_variant_env();
+  if (!vec) return 0;
+  if (v < 0) v = (Q > 32) ? 2 : 0;
+  if ((v == 3 || v == 4) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
+  return v;
 }
 
 static int ensure_carry(roc_sg_plan* plan, size_t ldFloats) {
@@ -773,6 +1072,18 @@ extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid
     PL_CUDA(cudaMemcpyAsync(&pl->numCarries, pl->carryIdx + pl->numChunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(&pl->numBig, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaStreamSynchronize(st));
+    if (pl->E) {
+      // rows the input matrix must have (1 + largest source id): the extent of the TMA tensor map
+      size_t tb3 = 0;
+      uint32_t maxSrc = 0;
+      cub::DeviceReduce::Max(nullptr, tb3, colSrc, dcount, (int64_t)pl->E, st);
+      if (tb3 > tb) { cudaFree(tmp); tmp = nullptr; PL_CUDA(cudaMalloc(&tmp, tb3)); }
+      PL_CUDA(cub::DeviceReduce::Max(tmp, tb3, colSrc, dcount, (int64_t)pl->E, st));
+      count_launch(2);
+      PL_CUDA(cudaMemcpyAsync(&maxSrc, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      PL_CUDA(cudaStreamSynchronize(st));
+      pl->inRows = (uint64_t)maxSrc + 1;
+    }
   }
 done:
 #undef PL_CUDA
@@ -808,8 +1119,11 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
   if (!pl || H <= 0 || !in || !out || ldIn < H || ldOut < H) return ROC_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
   const bool vec = (ldIn % 4 == 0) && (ldOut % 4 == 0) && aligned16(in) && aligned16(out);
-  // column blocks: the widest kernel covers 256 T-columns (1024 floats vectorised, 256 scalar)
-  const int blockCols = vec ? 1024 : 256;
+  // column blocks: the widest kernel covers 256 T-columns (1024 floats vectorised, 256 scalar);
+  // the TMA variants take 64 T-columns (a tensor-map box is at most 256 elements wide)
+  int variant = pick_variant(vec ? ((uint32_t)H + 3) / 4 : (uint32_t)H, vec);
+  if ((variant == 3 || variant == 4) && H > 256 && sg_variant_env() < 0) variant = 2;
+  const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4) ? 256 : 1024);
   {
     int need = H < blockCols ? H : blockCols;
     int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4);
@@ -822,15 +1136,33 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
     p.col = pl->col; p.in = in + c0; p.out = out + c0; p.carry = pl->carry;
     p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.numBig = pl->numBig; p.epi = epilogue;
     p.dense = (pl->nloc > 0 && pl->E / pl->nloc >= (uint32_t)SG_CH) ? 1 : 0;
+    SgLaunch how;
+    how.variant = variant; how.tcfg = sg_tcfg_env(); how.tmap = nullptr;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));     // only the gather4 kernels read it
+    how.tmap = &tm;
     int rc;
     if (vec) {
       p.ldIn = (size_t)ldIn / 4; p.ldOut = (size_t)ldOut / 4; p.ldC = pl->carryLd / 4;
       p.Q = ((uint32_t)hb + 3) / 4;
-      rc = dispatch<4>(p, st);
+      if (variant == 3) {
+        // tensor map of the input: [inRows][Q*4] floats, rows ldIn floats apart; the box is the worker's
+        // whole lane span (columns past Q*4 are zero-filled), one row per box — gather4 fetches four
+        const uint32_t span = p.Q <= 4 ? 4u : p.Q <= 8 ? 8u : p.Q <= 16 ? 16u : p.Q <= 32 ? 32u : 64u;
+        const uint64_t rowBytes = (uint64_t)p.Q * 16u;
+        const CUtensorMapL2promotion promo = rowBytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                            : rowBytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                              : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        if (!tc::make_tmap_32b_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, in + c0, pl->inRows, (uint64_t)p.Q * 4u,
+                                  (uint64_t)ldIn, 1u, span * 4u, CU_TENSOR_MAP_SWIZZLE_NONE, promo))
+          return ROC_ERR_UNSUPPORTED;
+        how.tmap = &tm;
+      }
+      rc = dispatch<4>(p, how, st);
     } else {
       p.ldIn = (size_t)ldIn; p.ldOut = (size_t)ldOut; p.ldC = pl->carryLd;
       p.Q = (uint32_t)hb;
-      rc = dispatch<1>(p, st);
+      rc = dispatch<1>(p, how, st);
     }
     if (rc != ROC_OK) return rc;
   }

@@ -182,7 +182,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 // fp32 row-major [rows][cols] with `ld` floats between rows; box = [boxRows][boxCols],
 // 128-byte swizzle (boxCols * 4 must be 128), out-of-bounds elements read as zero.
 inline bool make_tmap_32b_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols,
-                             uint64_t ld, uint32_t boxRows, uint32_t boxCols, CUtensorMapSwizzle swizzle) {
+                             uint64_t ld, uint32_t boxRows, uint32_t boxCols, CUtensorMapSwizzle swizzle,
+                             CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
@@ -190,7 +191,7 @@ inline bool make_tmap_32b_2d(CUtensorMap* m, CUtensorMapDataType dt, const void*
   cuuint32_t box[2] = {boxCols, boxRows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 inline bool make_tmap_f32_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,

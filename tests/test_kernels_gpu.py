@@ -62,6 +62,40 @@ def test_sg_planned_vs_oracle(kind, h):
     assert torch.equal(plan.forward(xp), got)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "rmat", "dense", "ragged", "single"])
+@pytest.mark.parametrize("h", [4, 16, 41, 64, 100, 128, 200, 256, 602])
+def test_sg_variants_are_bitwise_identical(kind, h, monkeypatch):
+    """The register (A), cp.async (C) and TMA gather4 / bulk-copy (T) kernels share the chunk plan and the
+    per-row summation order, so they must agree bit for bit — with every ring shape of variant T and with
+    the fused epilogue — and the TMA path must meet the oracle exactly like the others."""
+    row_end, col = graph(kind)
+    n = row_end.shape[0]
+    x = np.random.RandomState(h).randn(n, h).astype(np.float32)
+    d_re, d_col = to_dev(row_end, col)
+    plan = K.SgPlan(0, n - 1, 0, d_re, d_col)
+    xp = K.padded(n, h, DEV, fill=torch.from_numpy(x).to(DEV))
+    monkeypatch.setenv("ROC_SG_VARIANT", "a")
+    base = plan.forward(xp).clone()
+    base_e = plan.forward(xp, epilogue=_lib.SG_EPI_NORM | _lib.SG_EPI_RELU).clone()
+    rel_close(base.cpu().numpy(), oracle.scatter_gather(0, n - 1, 0, row_end, col, x), what="A %s H=%d" % (kind, h))
+    for variant, cfgs in (("c", [None]), ("t", [None, 1, 2, 3, 4, 5, 6]), ("b", [None, 1, 3])):
+        monkeypatch.setenv("ROC_SG_VARIANT", variant)
+        for cfg in cfgs:
+            if cfg is None:
+                monkeypatch.delenv("ROC_SG_TCFG", raising=False)
+            else:
+                monkeypatch.setenv("ROC_SG_TCFG", str(cfg))
+            got = plan.forward(xp)
+            got_e = plan.forward(xp, epilogue=_lib.SG_EPI_NORM | _lib.SG_EPI_RELU)
+            torch.cuda.synchronize()
+            assert torch.equal(got, base), "variant %s cfg %s differs from A (%s, H=%d)" % (variant, cfg, kind, h)
+            # as bit patterns: rows of degree 0 are 0 / sqrt(0) = NaN under the norm epilogue (quirk Q5)
+            assert torch.equal(got_e.contiguous().view(torch.int32), base_e.contiguous().view(torch.int32)), \
+                "variant %s cfg %s epilogue differs (%s, H=%d)" % (variant, cfg, kind, h)
+    monkeypatch.delenv("ROC_SG_TCFG", raising=False)
+    monkeypatch.delenv("ROC_SG_VARIANT", raising=False)
+
+
 @pytest.mark.parametrize("kind", ["uniform", "rmat", "dense"])
 def test_sg_epilogues(kind):
     row_end, col = graph(kind)
