@@ -1,27 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — GCN training edges/sec on synthetic R-MAT graphs (BASELINE.json metric).
+"""bench.py — GCN training edges/sec on synthetic graphs (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[1] at N = 1 — 2-layer GCN
-602 -> 64 -> 41 on an R-MAT scale-22 graph (2^22 vertices, 2^25 undirected pairs
-before symmetrisation + dedup + self loops, ~64M edges), dropout 0.5, Adam.
-For N > 1 the graph grows with N (scale 22 + log2 N, pairs 2^25 * N: weak
-scaling, the N = 8 point is configs[3]'s R-MAT scale-25 graph) and is
-vertex-range partitioned by the reference's own partitioner.
+Workloads (BASELINE.json `configs`, --config; the default, 2, is the one the metric is quoted on):
+  1  2-layer GCN 16-16-5 on a 1K-vertex / 10K-edge uniform graph (launch-bound)
+  2  2-layer GCN 602-64-41 on R-MAT scale 22 (+log2 N: weak scaling, 2^25 pairs per GPU)
+  3  3-layer GraphSAGE-mean 100-256-256-47 on a products-shaped graph (2.45M vertices / ~62M edges; strong scaling)
+  4  2-layer GCN 602-128-41 on R-MAT scale 22 + log2 N (the N = 8 point is the scale-25 graph; weak scaling)
+  5  4-layer GCN with the residual branch 602-256-256-256-41 on a Reddit-shaped graph (233K vertices / ~115M
+     edges; strong scaling)
+Graphs are symmetrised, given self loops and vertex-range partitioned by the reference's own partitioner.
 
-A "step" is one training epoch: zero_gradients + forward + backward + update
-(gnn.cc:103-106), everything resident in HBM.  `value` = total edges * steps /
-max-over-ranks device time (CUDA events on the engine's stream).  `e2e` = the same
-metric through the public API with HOST buffers: every step re-uploads the
-features / labels / mask from pinned host memory (H2D inside the timed region)
-and reads the loss metrics back (D2H).  `roofline` is the ScatterGather launch
-at H = 64 timed live with CUDA events inside the timed steps.  `cpu_baseline` /
-`--impl reference` time the CPU oracle (OpenMP, all host cores) on a bounded
-sample of the same workload — ROC ships no CPU kernels.
+A "step" is one training epoch: zero_gradients + forward + backward + update (gnn.cc:103-106), everything
+resident in HBM.  `value` = total edges * steps / max-over-ranks device time (CUDA events on the engine's
+stream).  `e2e` = the same metric through the public API with HOST buffers: every step re-uploads the
+features / labels / mask from pinned host memory (H2D inside the timed region) and reads the loss metrics back
+(D2H).  `roofline` is the ScatterGather launch at the hidden width, timed live with CUDA events inside the timed
+steps; `frac` is algorithmic bytes / time / peak (can exceed 1: hub rows are served by L2), `frac_dram` uses the
+DRAM traffic ncu measured for that (config, N) when profiles/sg_traffic.json has it.  `cpu_baseline` /
+`--impl reference` time the CPU oracle (OpenMP, all host cores, thread count set explicitly) on a bounded sample
+of the same workload — ROC ships no CPU kernels.  For N > 1 a `parity_check` (outside the timed
+region) trains a bounded graph on the N-rank engine and on a 1-rank engine and compares logits / loss / dW.
 """
 import argparse
+import importlib.util
 import json
 import math
 import os
@@ -35,16 +39,37 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LAYERS = [602, 64, 41]
 DROPOUT = 0.5
 LR, WD = 0.01, 0.0001          # example_run.sh: -lr 0.01 -decay 0.0001
 BASE_SCALE = 22
 BASE_PAIRS = 1 << 25
 CPU_SAMPLE_SCALE = 19          # cpu_baseline / reference arm: same generator, 1/8 of the vertices
 
+CONFIGS = {
+    1: dict(kind="gcn", layers=[16, 16, 5], graph="uniform", scaling="strong",
+            desc="2-layer GCN 16-16-5, uniform 1K vertices / 10K edges"),
+    2: dict(kind="gcn", layers=[602, 64, 41], graph="rmat", scaling="weak",
+            desc="2-layer GCN 602-64-41, R-MAT"),
+    3: dict(kind="sage", layers=[100, 256, 256, 47], graph="products", scaling="strong",
+            desc="3-layer GraphSAGE-mean 100-256-256-47, products-shaped power-law graph"),
+    4: dict(kind="gcn", layers=[602, 128, 41], graph="rmat", scaling="weak",
+            desc="2-layer GCN 602-128-41, R-MAT"),
+    5: dict(kind="gcn", layers=[602, 256, 256, 256, 41], graph="reddit", scaling="strong",
+            desc="4-layer GCN + residual branch 602-256-256-256-41, Reddit-shaped power-law graph"),
+}
+
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def datasets_module():
+    """roc_b200/datasets.py loaded as a plain file: the generators need only numpy + torch, and the reference
+    arm must not import the product package (its .so would show up in that arm's loaded libraries)."""
+    spec = importlib.util.spec_from_file_location("roc_synth_datasets", os.path.join(ROOT, "roc_b200", "datasets.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
@@ -103,11 +128,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_graph(scale, pairs, device):
+def make_graph(ds, cfg, world, device, scale_override=0):
+    """(row_end u64, col u32, label) of config `cfg` at `world` GPUs."""
     import torch
-    from roc_b200 import datasets
     t0 = time.time()
-    row_end, col = datasets.rmat_graph(scale, pairs, seed=1, device=device)
+    g = CONFIGS[cfg]["graph"]
+    if g == "uniform":
+        row_end, col = ds.uniform_graph(1000, 4500, seed=1, device=device)
+        label = "uniform 1K/10K"
+    elif g == "rmat":
+        scale = BASE_SCALE + int(round(math.log2(world)))
+        pairs = BASE_PAIRS * world
+        if scale_override:
+            scale, pairs = scale_override, 1 << (scale_override + 3)
+        row_end, col = ds.rmat_graph(scale, pairs, seed=1, device=device)
+        label = "R-MAT scale-%d" % scale
+    elif g == "products":      # configs[2]: 2.45M vertices, ~62M edges
+        row_end, col = ds.powerlaw_graph(2449029, 30_000_000, alpha=1.6, seed=1, device=device)
+        label = "products-shaped"
+    elif g == "reddit":        # configs[4]: 233K vertices, ~115M edges (mean degree ~490)
+        row_end, col = ds.powerlaw_graph(232965, 57_500_000, alpha=1.3, seed=1, device=device)
+        label = "Reddit-shaped"
+    else:
+        raise KeyError(g)
     if device != "cpu":
         torch.cuda.synchronize()
     re_h = row_end.cpu().numpy().astype(np.uint64)
@@ -115,8 +158,8 @@ def make_graph(scale, pairs, device):
     del row_end, col
     if device != "cpu":
         torch.cuda.empty_cache()
-    log("[bench] R-MAT scale %d: N=%d E=%d (%.1fs)" % (scale, re_h.shape[0], col_h.shape[0], time.time() - t0))
-    return re_h, col_h
+    log("[bench] %s: N=%d E=%d (%.1fs)" % (label, re_h.shape[0], col_h.shape[0], time.time() - t0))
+    return re_h, col_h, label
 
 
 def sg_bytes(n, e, h):
@@ -124,44 +167,67 @@ def sg_bytes(n, e, h):
     return e * (4 * h + 4) + n * (4 * h + 8)
 
 
+def sg_compulsory_bytes(n, e, h):
+    """Lower bound with perfect reuse of gathered rows: E*4 + N*(8 + 8H)."""
+    return e * 4 + n * (8 + 8 * h)
+
+
 # --------------------------------------------------------------------- CPU arm ---
-def cpu_epoch_rate(steps, warmup, device_for_gen):
-    """Oracle GCN epoch (fp32, OpenMP) on the bounded sample; returns (edges/s, ms/step, info)."""
+def cpu_epoch_rate(steps, warmup, layers):
+    """Oracle GCN epoch (fp32, OpenMP on every host core) on the bounded sample.
+    Returns (median edges/s, best edges/s, median ms/step, info)."""
+    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1; libgomp reads the environment when the oracle library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     from oracle import oracle
-    from roc_b200 import datasets
+    ds = datasets_module()
+    oracle.set_num_threads(cores)          # and set the team size explicitly as well
     pairs = BASE_PAIRS >> (BASE_SCALE - CPU_SAMPLE_SCALE)
-    re_h, col_h = make_graph(CPU_SAMPLE_SCALE, pairs, device_for_gen)
+    re_t, col_t = ds.rmat_graph(CPU_SAMPLE_SCALE, pairs, seed=1, device="cpu")
+    re_h, col_h = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
     n, e = re_h.shape[0], col_h.shape[0]
-    feats, labels, mask = datasets.node_data(n, LAYERS[0], LAYERS[-1], seed=1)
+    feats, labels, mask = ds.node_data(n, layers[0], layers[-1], seed=1)
     rng = np.random.RandomState(1)
-    ws = [((rng.rand(LAYERS[i + 1], LAYERS[i]).astype(np.float32) * 2 - 1) *
-           np.float32(math.sqrt(6.0 / (LAYERS[i] + LAYERS[i + 1])))) for i in range(len(LAYERS) - 1)]
-    m = oracle.GcnOracle(re_h, col_h, LAYERS, ws, lr=LR, weight_decay=WD, dropout=DROPOUT, acc64=False)
-    oh = datasets.onehot(labels.numpy(), LAYERS[-1])
+    dims = list(zip(layers[:-1], layers[1:]))
+    if len(layers) > 3:                     # residual branch: a second weight per layer (gnn.cc:86-90)
+        dims = [d for d in dims for _ in (0, 1)]
+    ws = [((rng.rand(o, i).astype(np.float32) * 2 - 1) * np.float32(math.sqrt(6.0 / (i + o)))) for (i, o) in dims]
+    m = oracle.GcnOracle(re_h, col_h, layers, ws, lr=LR, weight_decay=WD, dropout=DROPOUT, acc64=False)
+    oh = ds.onehot(labels.numpy(), layers[-1])
     f, mk = feats.numpy(), mask.numpy()
     for _ in range(warmup):
         m.train_epoch(f, oh, mk)
-    t0 = time.time()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         m.train_epoch(f, oh, mk)
-    dt = time.time() - t0
+        times.append(time.perf_counter() - t0)
+    med, best = float(np.median(times)), float(np.min(times))
     info = {"cores": oracle.num_threads(), "kind": "port",
-            "sample": "oracle GCN %s epoch (fp32, OpenMP) on R-MAT scale-%d (N=%d, E=%d), %d steps" %
-                      ("-".join(map(str, LAYERS)), CPU_SAMPLE_SCALE, n, e, steps)}
-    return e * steps / dt, 1e3 * dt / steps, info
+            "sample": "oracle GCN %s epoch (fp32, OpenMP) on R-MAT scale-%d (N=%d, E=%d), %d steps after %d warm-up; "
+                      "value = median, best_value = fastest step" %
+                      ("-".join(map(str, layers)), CPU_SAMPLE_SCALE, n, e, steps, warmup)}
+    return e / med, e / best, 1e3 * med, info
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    rate, ms, info = cpu_epoch_rate(steps, warm, "cpu")
+    cfg = CONFIGS[args.config]
+    layers = cfg["layers"] if cfg["kind"] == "gcn" else CONFIGS[2]["layers"]
+    steps = max(5, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    rate, best, ms, info = cpu_epoch_rate(steps, warm, layers)
     info["value"] = rate
+    info["best_value"] = best
+    info["unit"] = "edges/s"
     line = {"impl": "reference", "metric": "gcn_training_edges_per_sec", "value": rate, "unit": "edges/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "2-layer GCN 602-64-41, R-MAT (bounded sample: scale %d)" % CPU_SAMPLE_SCALE,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s (bounded CPU sample: R-MAT scale %d; the GPU arm runs the full-size graph — "
+                                   "a rate metric)" % (cfg["desc"], CPU_SAMPLE_SCALE),
                        "note": "ROC ships CUDA-only kernels and cannot be built here (Legion absent); the reference "
                                "arm is the CPU restatement of its algorithm (oracle/) on all host cores"},
             "cpu_baseline": info,
@@ -171,23 +237,92 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------- GPU arm ---
+def build_model(m, cfg):
+    from roc_b200.model import build_gcn, build_sage_mean
+    c = CONFIGS[cfg]
+    if c["kind"] == "gcn":
+        return build_gcn(m, c["layers"], DROPOUT, lr=LR, weight_decay=WD)
+    return build_sage_mean(m, c["layers"], DROPOUT, lr=LR, weight_decay=WD)
+
+
+def parity_check(rank, local_rank, world, dist, dev):
+    """N-rank engine vs 1-rank engine on a bounded graph (R-MAT scale 16, GCN 64-32-16-8 incl. the residual
+    branch, dropout 0.5): stitched logits, loss and all-reduced dW of the first step at 1e-4 relative
+    (+1e-5 * max|x| for cancellation).  Runs outside every timed region; every rank takes part."""
+    import torch
+    from roc_b200 import datasets
+    from roc_b200.model import Host, Model, build_gcn
+    layers = [64, 32, 16, 8]
+    re_t, col_t = datasets.rmat_graph(16, 1 << 19, seed=7, device=dev)
+    re_h, col_h = re_t.cpu().numpy().astype(np.uint64), col_t.cpu().numpy().astype(np.uint32)
+    n = re_h.shape[0]
+    feats, labels, mask = datasets.node_data(n, layers[0], layers[-1], seed=3)
+    feats, labels, mask = feats.numpy(), labels.numpy(), mask.numpy().astype(np.int32)
+
+    def run(host):
+        host.graph_from_arrays(re_h, col_h)
+        info = host.graph_info()
+        rl, rr = info["rowLeft"], info["rowRight"]
+        m = Model(host, seed=1)
+        h = build_gcn(m, layers, 0.5, lr=LR, weight_decay=WD)
+        m.set_tensor(h["input"], feats[rl:rr + 1])
+        m.set_labels(h["label"], labels[rl:rr + 1])
+        m.set_tensor(h["mask"], mask[rl:rr + 1])
+        m.train_mode(); m.zero_gradients(); m.forward()
+        logits = m.get_tensor(h["logits"])
+        m.backward()
+        perf = m.metrics()
+        m.update()
+        dw = [m.get_parameter(p, "grad") for p in range(m.num_parameters())]
+        host.close()
+        return rl, rr, logits, perf, dw
+
+    host = Host(local_rank, rank, world)
+    uid = [Host.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    host.nccl_init(uid[0])
+    rl, rr, logits, perf, dw = run(host)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rl, rr, logits, perf["trainLoss"], perf["trainAll"]))
+    if rank != 0:
+        return None
+    _, _, logits1, perf1, dw1 = run(Host(local_rank, 0, 1))
+    stitched = np.concatenate([g[2] for g in sorted(gathered, key=lambda g: g[0])])
+
+    def rel_err(a, b):
+        """max |a-b| / (|b| + 0.1 * max|b|): at most 1e-4 when a matches b to 1e-4 relative + 1e-5 * max|b| absolute."""
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        return float((np.abs(a - b) / (np.abs(b) + 0.1 * np.abs(b).max() + 1e-30)).max())
+    errs = {"logits": rel_err(stitched, logits1),
+            "loss": abs(sum(g[3] for g in gathered) - perf1["trainLoss"]) / abs(perf1["trainLoss"]),
+            "dW": max(rel_err(a, b) for a, b in zip(dw, dw1))}
+    ok = (errs["logits"] <= 1e-4 and errs["loss"] <= 1e-4 and errs["dW"] <= 1e-4 and
+          sum(g[4] for g in gathered) == perf1["trainAll"] and stitched.shape == logits1.shape)
+    return {"ranks": world, "graph": "R-MAT scale-16 (N=%d, E=%d)" % (n, col_h.shape[0]), "model": "GCN 64-32-16-8 + residual, dropout 0.5",
+            "max_rel_err": max(errs.values()), "errs": errs, "tolerance": 1e-4, "ok": bool(ok)}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from roc_b200 import _lib, datasets
-    from roc_b200.model import Host, Model, build_gcn
+    from roc_b200.model import Host, Model
 
     _lib.require_device()
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    cfg = CONFIGS[args.config]
+    layers = cfg["layers"]
 
-    scale = BASE_SCALE + int(round(math.log2(world)))
-    pairs = BASE_PAIRS * world
-    if args.scale:
-        scale, pairs = args.scale, (1 << (args.scale + 3)) * 1
-    re_h, col_h = make_graph(scale, pairs, dev)
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_check(rank, local_rank, world, dist, dev)
+        if rank == 0:
+            log("[bench] parity_check: %s" % json.dumps(parity))
+
+    re_h, col_h, glabel = make_graph(datasets, args.config, world, dev, args.scale)
     n, e = re_h.shape[0], col_h.shape[0]
 
     host = Host(local_rank, rank, world)
@@ -200,17 +335,17 @@ def run_ours(args, rank, local_rank, world):
     rl, rr = info["rowLeft"], info["rowRight"]
     nloc = rr - rl + 1
     m = Model(host, seed=1)
-    hnd = build_gcn(m, LAYERS, DROPOUT, lr=LR, weight_decay=WD)
+    hnd = build_model(m, args.config)
 
     # synthetic node data: pinned host copies (e2e uploads them every step) of this rank's rows
     g = torch.Generator(device="cpu"); g.manual_seed(1000 + rank)
-    feats = torch.empty((nloc, LAYERS[0]), dtype=torch.float32, pin_memory=True)
+    feats = torch.empty((nloc, layers[0]), dtype=torch.float32, pin_memory=True)
     chunk = 1 << 18
     dg = torch.Generator(device=dev); dg.manual_seed(1000 + rank)
     for a in range(0, nloc, chunk):
         b = min(nloc, a + chunk)
-        feats[a:b].copy_(torch.rand((b - a, LAYERS[0]), device=dev, generator=dg) * 2 - 1)
-    labels = torch.randint(0, LAYERS[-1], (nloc,), generator=g, dtype=torch.int32).pin_memory()
+        feats[a:b].copy_(torch.rand((b - a, layers[0]), device=dev, generator=dg) * 2 - 1)
+    labels = torch.randint(0, layers[-1], (nloc,), generator=g, dtype=torch.int32).pin_memory()
     u = torch.rand(nloc, generator=g)
     mask = torch.full((nloc,), 2, dtype=torch.int32)
     mask[u < 0.76] = 1
@@ -227,6 +362,9 @@ def run_ours(args, rank, local_rank, world):
     d2h = 28   # sizeof(PerfMetrics)
 
     stream = torch.cuda.ExternalStream(host.stream, device=dev)
+    # configs whose working set fits in the 126 MB L2 (config 1) get an L2 flush between timed steps
+    small = (nloc * (layers[0] + 2 * max(layers[1:])) * 4 + e * 4) < (256 << 20)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
 
     def barrier():
         host.synchronize()
@@ -235,20 +373,29 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """K steps between one pair of events (the contract's number) and, separately, per-step events for
+        median / best.  With an L2 flush between steps only the per-step events are meaningful."""
         barrier()
+        per = []
         with torch.cuda.stream(stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]
             e0.record(stream)
-            for _ in range(steps):
+            for i in range(steps):
+                if flush is not None:
+                    flush.zero_()
+                marks[2 * i].record(stream)
                 fn()
+                marks[2 * i + 1].record(stream)
             e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        per = [marks[2 * i].elapsed_time(marks[2 * i + 1]) for i in range(steps)]
+        ms = sum(per) if flush is not None else e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms] + per, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms
+            ms, per = float(t[0]), [float(v) for v in t[1:]]
+        return ms, per
 
     # ---- resident-in-HBM arm
     for _ in range(max(args.warmup, 3)):
@@ -258,7 +405,7 @@ def run_ours(args, rank, local_rank, world):
         sampler.start()
     m.profile_sg(True)
     l0 = _lib.lib.roc_launch_count()
-    ms_total = timed(m.train_epoch, args.steps)
+    ms_total, per_step = timed(m.train_epoch, args.steps)
     launches = _lib.lib.roc_launch_count() - l0
     sg_times = m.profile_sg_read()
     m.profile_sg(False)
@@ -276,75 +423,93 @@ def run_ours(args, rank, local_rank, world):
         ms_e2e, e2e_value = float("nan"), None
     else:
         e2e_step()
-        ms_e2e = timed(e2e_step, e2e_steps)
+        ms_e2e, _ = timed(e2e_step, e2e_steps)
         e2e_value = e * e2e_steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel: ScatterGather at H = 64 on this rank's partition
+    # ---- roofline of the dominant kernel: ScatterGather at the hidden width on this rank's partition
     eloc = info["colRight"] - info["colLeft"] + 1
-    sg64 = [t for (h, t) in sg_times if h == LAYERS[1]]
+    hsg = layers[1]
+    sgh = [t for (h, t) in sg_times if h == hsg]
     peak, peak_src = peaks()
     roof = None
-    if sg64:
-        t_avg = sum(sg64) / len(sg64)
-        ach = sg_bytes(nloc, eloc, LAYERS[1]) / (t_avg * 1e-3) / 1e9
-        traffic = None
+    if sgh:
+        t_avg = sum(sgh) / len(sgh)
+        ach = sg_bytes(nloc, eloc, hsg) / (t_avg * 1e-3) / 1e9
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "sg_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tab = json.load(open(tp)).get("per_config", {})
+                ent = tab.get("cfg%d_n%d" % (args.config, world))
+                if ent:
+                    traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "kernel": "sg_chunk_kernel<float4,L=16> (+fix-up) H=%d" % LAYERS[1], "launch_ms": t_avg,
-                "launches_timed": len(sg64), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": sg_bytes(nloc, eloc, LAYERS[1]),
-                # the algorithmic bytes are mostly neighbour-row gathers and 59 % of those sectors hit
-                # in L2 (hub rows), so `frac` can exceed 1; this one uses the ncu DRAM traffic instead
-                "frac_dram": (traffic / (t_avg * 1e-3) / 1e9 / peak) if (traffic and world == 1) else None}
+                "traffic_source": traffic_src,
+                "kernel": "ScatterGather main kernel (+fix-up) H=%d" % hsg, "launch_ms": t_avg,
+                "launch_ms_best": min(sgh), "launches_timed": len(sgh), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sg_bytes(nloc, eloc, hsg),
+                "compulsory_bytes_per_launch": sg_compulsory_bytes(nloc, eloc, hsg),
+                "frac_compulsory": sg_compulsory_bytes(nloc, eloc, hsg) / (t_avg * 1e-3) / 1e9 / peak,
+                # the algorithmic bytes are mostly neighbour-row gathers and most of those sectors hit in L2
+                # (hub rows), so `frac` can exceed 1; this one uses the ncu DRAM traffic of this (config, N)
+                "frac_dram": (traffic / (t_avg * 1e-3) / 1e9 / peak) if traffic else None}
     sg_share = sum(t for _, t in sg_times) / ms_total if sg_times else None
 
     # ---- side columns (rank 0, N = 1 only): CPU oracle + the reference's own kernel on this GPU
     cpu = None
     refk = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        try:
-            rate, _, cinfo = cpu_epoch_rate(1, 0, dev)
-            cinfo["value"] = rate
-            cinfo["unit"] = "edges/s"
-            cpu = cinfo
-        except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
-            cpu = {"error": repr(ex)}
-        try:
-            refk = reference_kernel_column(re_h, col_h, dev)
-        except Exception as ex:
-            refk = {"error": repr(ex)}
+        if cfg["kind"] == "gcn":
+            try:
+                rate, best, _, cinfo = cpu_epoch_rate(3, 1, layers)
+                cinfo["value"] = rate
+                cinfo["best_value"] = best
+                cinfo["unit"] = "edges/s"
+                cpu = cinfo
+            except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
+                cpu = {"error": repr(ex)}
+        if hsg <= 512 and n * hsg < (1 << 31):
+            try:
+                refk = reference_kernel_column(re_h, col_h, dev, h=hsg)
+            except Exception as ex:
+                refk = {"error": repr(ex)}
 
     if rank == 0:
+        per_sorted = sorted(per_step)
         line = {"metric": "gcn_training_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step_median": per_sorted[len(per_sorted) // 2], "ms_per_step_best": per_sorted[0],
+                "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "2-layer GCN %s, R-MAT scale-%d (N=%d, E=%d incl. self loops), dropout %.1f, Adam"
-                                       % ("-".join(map(str, LAYERS)), scale, n, e, DROPOUT),
+                "config": {"workload": "%s, %s (N=%d, E=%d incl. self loops), dropout %.1f, Adam"
+                                       % (cfg["desc"], glabel, n, e, DROPOUT),
+                           "baseline_config": args.config,
                            "parallelism": "vertex-range dp%d" % world,
-                           "l2": "inputs larger than L2 (features %.1f GB/GPU, graph %.2f GB)" %
-                                 (nloc * 604 * 4 / 1e9, (e * 4 + n * 8) / 1e9)},
+                           "l2": ("L2 flushed (256 MB write) before every timed step" if flush is not None else
+                                  "inputs larger than L2 (features %.1f GB/GPU, graph %.2f GB)" %
+                                  (nloc * round_up4(layers[0]) * 4 / 1e9, (e * 4 + n * 8) / 1e9))},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu,
                 "sg_share_of_step": sg_share, "reference_kernel": refk,
-                "train_loss": perf["trainLoss"], "plan": host.plan_info()}
+                "train_loss": perf["trainLoss"], "plan": host.plan_info(), "parity_check": parity}
         print(json.dumps(line), flush=True)
     host.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def round_up4(x):
+    return (x + 3) // 4 * 4
+
+
 def reference_kernel_column(row_end_h, col_h, dev, h=64, iters=5):
     """The reference's own aggre_coop_kernel (cut from scattergather_kernel.cu:20-76 into oracle/_ref) on
-    the same graph and GPU, H = 64, HBM-resident buffers, the reference's grid.  It omits the reference's
+    the same graph and GPU, HBM-resident buffers, the reference's grid.  It omits the reference's
     per-call PCIe staging (types.cu:28, scattergather_kernel.cu:145-157): an upper bound for ROC."""
     import torch
     from oracle import ref
@@ -376,9 +541,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[n-1]")
     ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank parity check (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -160,6 +160,16 @@ void roc_halo_destroy(roc_halo* h);
 uint32_t roc_halo_size(const roc_halo* h);
 const roc_vid_t* roc_halo_ids(const roc_halo* h);         /* device */
 const roc_vid_t* roc_halo_col_local(const roc_halo* h);   /* device */
+/* Host-side bookkeeping of the exchange (HOST pointers, no device work).  recv: the sorted halo ids are
+ * grouped by owner (partitions are contiguous id ranges, host_vbounds as in roc_partition):
+ * recvOffs[q] / recvCounts[q] = first halo row owned by partition q / how many; ROC_ERR_INVALID if the
+ * list is not strictly increasing, leaves every range, or names one of this partition's own rows.
+ * send: host_allCounts[q * P + r] = rows partition q requests from owner r (every rank's recvCounts,
+ * all-gathered); this rank packs the rows q asked of it for q = 0..P-1 in order. */
+int roc_halo_recv_layout(uint32_t nHalo, const roc_vid_t* host_ids, int numParts, int myPart,
+                         const roc_vid_t* host_vbounds, uint64_t* recvCounts, uint64_t* recvOffs);
+int roc_halo_send_layout(int numParts, int myPart, const int32_t* host_allCounts, uint64_t* sendCounts,
+                         uint64_t* sendOffs, uint64_t* numSendRows);
 /* dst[j][0:H] = src[rows[j]][0:H]: packs the rows another partition asked for into a send buffer. */
 int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const float* src, int64_t ldSrc,
                   float* dst, int64_t ldDst, roc_stream_t stream);

@@ -68,13 +68,9 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   recvCounts.assign((size_t)P, 0); recvOffs.assign((size_t)P, 0);
   sendCounts.assign((size_t)P, 0); sendOffs.assign((size_t)P, 0);
   {
-    size_t k = 0;   // the halo is sorted by global id == grouped by owner (contiguous ranges)
-    for (int q = 0; q < P; q++) {
-      recvOffs[(size_t)q] = k;
-      while (k < numHalo && hid[k] <= vbounds[2 * q + 1]) k++;
-      recvCounts[(size_t)q] = k - recvOffs[(size_t)q];
-    }
-    ROC_ASSERT(k == numHalo && recvCounts[(size_t)me] == 0);
+    std::vector<uint64_t> rc((size_t)P), ro((size_t)P);
+    ROC_CHECK(roc_halo_recv_layout(numHalo, hid.data(), P, me, vbounds.data(), rc.data(), ro.data()));
+    for (int q = 0; q < P; q++) { recvCounts[(size_t)q] = (size_t)rc[(size_t)q]; recvOffs[(size_t)q] = (size_t)ro[(size_t)q]; }
   }
   // everyone learns everyone's request counts (P x P matrix), then the id lists travel to their owners
   int* d_cnt = (int*)rt->dmalloc(sizeof(int) * (size_t)P * (size_t)(P + 1));
@@ -84,11 +80,12 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   ROC_CHECK(rt->comm.allgather_i32(d_cnt, d_cnt + P, (size_t)P, rt->stream));
   ROC_CHECK(cudaMemcpyAsync(all.data(), d_cnt + P, sizeof(int) * (size_t)P * P, cudaMemcpyDeviceToHost, rt->stream));
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
-  numSendRows = 0;
-  for (int q = 0; q < P; q++) {
-    sendOffs[(size_t)q] = numSendRows;
-    sendCounts[(size_t)q] = (size_t)all[(size_t)q * P + me];   // rows of mine that partition q reads
-    numSendRows += sendCounts[(size_t)q];
+  {
+    std::vector<uint64_t> sc((size_t)P), so((size_t)P);
+    uint64_t total = 0;
+    ROC_CHECK(roc_halo_send_layout(P, me, all.data(), sc.data(), so.data(), &total));
+    for (int q = 0; q < P; q++) { sendCounts[(size_t)q] = (size_t)sc[(size_t)q]; sendOffs[(size_t)q] = (size_t)so[(size_t)q]; }
+    numSendRows = (size_t)total;
   }
   d_sendRows = (V_ID*)rt->dmalloc(sizeof(V_ID) * (numSendRows ? numSendRows : 1));
   ROC_CHECK(rt->comm.alltoallv(roc_halo_ids(halo), recvCounts, recvOffs, d_sendRows, sendCounts, sendOffs,
@@ -160,4 +157,42 @@ Graph::Graph(Context ctx, Runtime* /*runtime*/, V_ID _numNodes, E_ID _numEdges, 
   if (roc_partition(numNodes, numEdges, numParts, host_rowEnd, vb.data(), eb.data(), &nr) != ROC_OK)
     ROC_FATAL("partitioner did not produce numParts ranges (gnn.cc:829)");
   build(ctx, host_rowEnd, host_colSrc ? host_colSrc + eb[2 * myPart] : nullptr);
+}
+
+// ---- host-side bookkeeping of the halo exchange (plain C ABI, host pointers; no device work) ----
+// The sorted halo id list is grouped by owner because partitions are contiguous vertex ranges:
+// recvOffs[q] = index of the first halo row owned by partition q, recvCounts[q] = how many.
+extern "C" int roc_halo_recv_layout(uint32_t nHalo, const roc_vid_t* host_ids, int numParts, int myPart,
+                                    const roc_vid_t* host_vbounds, uint64_t* recvCounts, uint64_t* recvOffs) {
+  if (numParts <= 0 || myPart < 0 || myPart >= numParts || !host_vbounds || !recvCounts || !recvOffs) return ROC_ERR_INVALID;
+  if (nHalo && !host_ids) return ROC_ERR_INVALID;
+  uint64_t k = 0;
+  for (int q = 0; q < numParts; q++) {
+    recvOffs[q] = k;
+    while (k < nHalo && host_ids[k] <= host_vbounds[2 * q + 1]) {
+      if (host_ids[k] < host_vbounds[2 * q]) return ROC_ERR_INVALID;      // not sorted / not inside any range
+      if (k > 0 && host_ids[k] <= host_ids[k - 1]) return ROC_ERR_INVALID; // must be strictly increasing
+      k++;
+    }
+    recvCounts[q] = k - recvOffs[q];
+  }
+  if (k != nHalo || recvCounts[myPart] != 0) return ROC_ERR_INVALID;       // an own row is never a halo row
+  return ROC_OK;
+}
+
+// allCounts[q * P + r] = rows partition q requests from owner r (every rank's recvCounts, all-gathered).
+// This rank (me) packs, for q = 0..P-1 in order, the rows q asked of it: sendCounts[q] = allCounts[q][me].
+extern "C" int roc_halo_send_layout(int numParts, int myPart, const int32_t* host_allCounts, uint64_t* sendCounts,
+                                    uint64_t* sendOffs, uint64_t* numSendRows) {
+  if (numParts <= 0 || myPart < 0 || myPart >= numParts || !host_allCounts || !sendCounts || !sendOffs) return ROC_ERR_INVALID;
+  uint64_t total = 0;
+  for (int q = 0; q < numParts; q++) {
+    const int32_t c = host_allCounts[(size_t)q * numParts + myPart];
+    if (c < 0 || (q == myPart && c != 0)) return ROC_ERR_INVALID;
+    sendOffs[q] = total;
+    sendCounts[q] = (uint64_t)c;
+    total += (uint64_t)c;
+  }
+  if (numSendRows) *numSendRows = total;
+  return ROC_OK;
 }

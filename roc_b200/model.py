@@ -244,3 +244,38 @@ def build_gcn(model, layers, dropout_rate, lr=0.01, weight_decay=0.05):
     model.adam(lr, weight_decay)
     model.init()
     return {"input": x, "label": label, "mask": mask, "logits": t, "relu_outs": relu_outs}
+
+
+def build_sage_mean(model, layers, dropout_rate, lr=0.01, weight_decay=0.05):
+    """GraphSAGE with the mean aggregator (BASELINE.json configs[2]) composed from the reference's own ops
+    (gnn.h:165-179; AGGR_AVG is declared at gnn.h:75-80 but the reference's ScatterGather only sums):
+
+        D    = dropout(t)
+        nb   = indegree_norm(indegree_norm(scatter_gather(linear(D, d_i))))    # D^-1 A (D W_nb): the mean over
+                                                                               # N(v) + v (self loops are in A)
+        t    = add(nb, linear(D, d_i))                                         # + the root / self weight
+        t    = relu(t)                                                         # all but the last layer
+
+    x / sqrt(deg) / sqrt(deg) is the mean to within one fp32 rounding.  Same wiring as the reference's residual
+    GCN layer (gnn.cc:79-90) with both norms after the aggregation."""
+    L = len(layers)
+    x = model.create_node_tensor(layers[0])
+    label = model.create_node_tensor(layers[-1])
+    mask = model.create_node_tensor(1, is_int=True)
+    t = x
+    relu_outs = []
+    for i in range(1, L):
+        d = model.dropout(t, dropout_rate)
+        nb = model.linear(d, layers[i], _lib.AC_MODE_NONE)
+        nb = model.scatter_gather(nb)
+        nb = model.indegree_norm(nb)
+        nb = model.indegree_norm(nb)
+        root = model.linear(d, layers[i], _lib.AC_MODE_NONE)
+        t = model.add(nb, root)
+        if i != L - 1:
+            t = model.relu(t)
+            relu_outs.append(t)
+    model.softmax_cross_entropy(t, label, mask)
+    model.adam(lr, weight_decay)
+    model.init()
+    return {"input": x, "label": label, "mask": mask, "logits": t, "relu_outs": relu_outs}

@@ -238,7 +238,7 @@ int main(int argc, char** argv) {
       report(nm, timeit([&] { k_tma<1, 0><<<grid, 128, smem>>>(tm, tab, idx, nIdx, rowB, t.D, t.G4, sink); }));
     }
 
-    struct RC { int R, W, bps; } rcs[] = {{6, 3, 2}, {4, 2, 3}, {2, 1, 6}, {3, 3, 4}, {2, 2, 6}};   // R % W == 0: a worker always reuses its own slots
+    struct RC { int R, W, bps; } rcs[] = {{6, 3, 2}, {4, 2, 3}, {2, 1, 6}, {2, 2, 6}};   // R % W == 0: a worker always reuses its own slots
     for (auto& t : rcs) {
       const size_t smem = (size_t)t.R * 64 * rowB + (size_t)t.R * 16;
       if (smem * t.bps > 222 * 1024 || smem > 220 * 1024) continue;
