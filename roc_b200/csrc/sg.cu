@@ -51,6 +51,7 @@ struct roc_sg_plan {
   float* carry = nullptr;         // [numCarries][carryLd]
   size_t carryLd = 0;
   uint64_t inRows = 1;            // 1 + largest source id in col: the rows a TMA tensor map of the input spans
+  uint32_t* desc = nullptr;       // [numChunks][8] per-chunk start state of the ring kernel (k_chunk_desc)
   int device = 0;
 };
 
@@ -103,6 +104,47 @@ __global__ void k_heavy_flag(uint32_t nloc, const uint32_t* __restrict__ rs, uin
   const uint32_t carries = heavy ? (t - 1) / SG_CH - s / SG_CH : 0;
   flag[r] = (heavy && carries <= 32u) ? 1 : 0;      // 32 == SG_BIG
   bigFlag[r] = (carries > 32u) ? 1 : 0;
+}
+
+// Start state of the worker that owns chunk c, so that the ring kernel reads ONE 32-byte record instead
+// of walking firstRow -> rs -> rs (three dependent global loads per chunk):
+//   [0] eb  first edge the worker processes     [1] ee  one past its last edge
+//   [2] cur first row it accumulates into        [3] curS = rs[cur]   [4] curT = rs[cur + 1]
+//   [5] r1  one past its last owned row          [6] flags: 1 = carry-in (cur is a heavy row owned by an
+//       earlier chunk), 2 = nothing to do        [7] carry slot of a carry-in part
+__global__ void k_chunk_desc(uint32_t numChunks, uint32_t E, const uint32_t* __restrict__ rs,
+                             const uint32_t* __restrict__ firstRow, const uint32_t* __restrict__ carryIdx,
+                             uint32_t* __restrict__ desc) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= numChunks) return;
+  constexpr uint32_t CH = SG_CH;
+  const uint32_t cb = w * CH, ce = min(cb + CH, E);
+  const uint32_t r0 = firstRow[w], r1 = firstRow[w + 1];
+  uint32_t eb = cb, ee = cb, cur = r0, curS = 0, curT = 0, flags = 0, segEnd = cb;
+  bool carryIn = false;
+  if (r0 > 0) {
+    const uint32_t pe = rs[r0], ps = rs[r0 - 1];
+    if (pe > cb && pe - ps > CH) {
+      carryIn = true; cur = r0 - 1; curS = ps; curT = pe; eb = cb; segEnd = min(pe, ce); flags = 1u;
+    }
+  }
+  if (!carryIn) {
+    if (r0 >= r1) { flags = 2u; }
+    else {
+      cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; eb = curS;
+      segEnd = (curT - curS > CH) ? min(curT, ce) : curT;
+    }
+  }
+  if (r1 > r0) {
+    const uint32_t s = rs[r1 - 1], t = rs[r1];
+    ee = (t - s > CH) ? min(t, ce) : t;
+  } else {
+    ee = segEnd;
+  }
+  if (flags & 2u) { eb = cb; ee = cb; }
+  uint4* d = reinterpret_cast<uint4*>(desc + (size_t)w * 8);
+  d[0] = make_uint4(eb, ee, cur, curS);
+  d[1] = make_uint4(curT, r1, flags, carryIdx[w]);
 }
 
 // ----------------------------------------------------------- vector helper ---
@@ -159,6 +201,8 @@ struct SgParams {
   uint32_t E, numChunks, numHeavy, numBig;
   int epi;
   int dense;           // mean degree >= chunk size: nearly every row is cut at chunk boundaries
+  const uint32_t* desc; // [numChunks][8] chunk start records (ring kernel)
+  uint32_t nloc;        // rows of the partition (rs has nloc + 1 entries)
 };
 
 // out[v] = relu?(acc / sqrtf(deg)) — what the model applies right after
@@ -201,37 +245,21 @@ sg_chunk_kernel(const SgParams p) {
 
   const uint32_t cb = w * CH;
   const uint32_t ce = min(cb + CH, p.E);
-  const uint32_t r0 = p.firstRow[w], r1 = p.firstRow[w + 1];
 
-  // current segment state
-  uint32_t cur;           // row id of the current segment
-  uint32_t curS, curT;    // its [start, end) in the edge array
-  uint32_t segEnd;        // where this worker stops accumulating into it
-  int kind;               // 0 = carry-in part of a heavy row, 1 = complete row, 2 = cut heavy row
-  uint32_t e;             // next edge
-
-  bool carryIn = false;
-  if (r0 > 0) {
-    uint32_t pe = rs[r0], ps = rs[r0 - 1];
-    if (pe > cb && pe - ps > CH) {
-      carryIn = true;
-      cur = r0 - 1; curS = ps; curT = pe; kind = 0; e = cb; segEnd = min(pe, ce);
-    }
-  }
-  if (!carryIn) {
-    if (r0 >= r1) return;  // nothing owned, nothing carried
-    cur = r0; curS = rs[r0]; curT = rs[r0 + 1]; e = curS;
-    bool heavy = curT - curS > CH;
-    segEnd = heavy ? min(curT, ce) : curT;
-    kind = heavy ? 2 : 1;
-  }
-  uint32_t ee;            // end of this worker's whole edge range
-  if (r1 > r0) {
-    uint32_t s = rs[r1 - 1], t = rs[r1];
-    ee = (t - s > CH) ? min(t, ce) : t;
-  } else {
-    ee = segEnd;
-  }
+  // The worker's start state comes from the plan's 32-byte chunk record (k_chunk_desc) — one load instead of
+  // the dependent walk firstRow[w] -> rs[r0], rs[r0 - 1] -> ... that cost every worker three round trips
+  // before its first gather (r2: ~7 % of a warp's lifetime).
+  const uint4 dA = __ldg(reinterpret_cast<const uint4*>(p.desc) + 2 * (size_t)w);
+  const uint4 dB = __ldg(reinterpret_cast<const uint4*>(p.desc) + 2 * (size_t)w + 1);
+  if (dB.z & 2u) return;           // nothing owned, nothing carried
+  uint32_t cur = dA.z;             // row id of the current segment
+  uint32_t curS = dA.w, curT = dB.x;   // its [start, end) in the edge array
+  uint32_t e = dA.x;               // next edge
+  const uint32_t ee = dA.y;        // end of this worker's whole edge range
+  const uint32_t r1 = dB.y;
+  const uint32_t carrySlot = dB.w;
+  int kind = (dB.z & 1u) ? 0 : ((curT - curS > CH) ? 2 : 1);   // 0 = carry-in part of a heavy row, 1 = complete row, 2 = cut heavy row
+  uint32_t segEnd = (kind == 1) ? curT : min(curT, ce);        // where this worker stops accumulating into it
 
   T acc[NCH];
 #pragma unroll
@@ -242,7 +270,7 @@ sg_chunk_kernel(const SgParams p) {
   // instruction-fetch bound (ncu: stalled_no_instruction 22.9 per issue, r1 run 2).
   auto flush = [&]() {
     char* dstb = (kind == 0)
-        ? reinterpret_cast<char*>(reinterpret_cast<T*>(p.carry) + lane) + (uint64_t)p.carryIdx[w] * ((uint32_t)p.ldC * (uint32_t)sizeof(T))
+        ? reinterpret_cast<char*>(reinterpret_cast<T*>(p.carry) + lane) + (uint64_t)carrySlot * ((uint32_t)p.ldC * (uint32_t)sizeof(T))
         : reinterpret_cast<char*>(out + lane) + (uint64_t)cur * ((uint32_t)p.ldOut * (uint32_t)sizeof(T));
     T* dst = reinterpret_cast<T*>(dstb);
     const int epi = (kind == 1) ? p.epi : 0;
@@ -740,6 +768,254 @@ sg_chunk_kernel_t(const SgParams p, const __grid_constant__ CUtensorMap tmap) {
   while (cur + 1 < r1) { advance(); flush(); }
 }
 
+// ------------------------------------------------- main kernel, variant R ---
+// Producer / consumer ring.  What the measurements of r2 asked for (tools/gather_ceiling.cu, B200):
+//  * the gather of this graph's row mix (69 % of the row fetches hit L2) is latency-bound: the pure
+//    LDG.128 gather reaches 38 B/clk/SM with variant A's 8 rows x 32 warps in flight and 58 with twice
+//    the warps — more requests outstanding than the register file can hold;
+//  * a shared-memory ring filled by `cp.async.bulk.tensor ... tile::gather4` sustains 55-60 B/clk/SM at
+//    that mix when (a) ~190 KB per SM are in flight, (b) the index loads never sit on the issue path
+//    and (c) several warps per SM issue: one UTMALDG costs its warp ~68 cycles (an ELECT / R2UR loop per
+//    lane), 15 B/clk per issuing warp at 1 KB per instruction.
+// So: a CTA is ONE producer warp and TWO worker warps that share a two-slot ring; six CTAs per SM for rows
+// of up to 256 bytes.  A slot holds one 64-edge chunk of gathered rows (64 x SLOTB bytes) and completes on
+// one `full` mbarrier.  The CTA walks a contiguous range of chunk pairs; worker h owns the chunks of parity
+// h and slot h holds them.  The producer's lane j (of half-warp h) holds the four source ids of gather4 #j
+// of its chunk in registers — one coalesced LDG.128 per lane, loaded one pair ahead — and issues it as soon
+// as the slot's `empty` barrier says both readers are done.
+// Readers of a slot: the chunk's own worker, and the worker of the PREVIOUS chunk, whose last rows may run
+// up to 63 edges into it (rows of degree <= 64 are finished by their owner).  Each of the two arrives on
+// `empty` (count 2) after it has waited on `full` for that use, so every waiter sees every phase of the
+// barriers it uses (a parity wait can only be one phase ahead).
+// A worker is a whole warp: lane l owns VW consecutive floats of the row (float2 for rows of up to 64
+// floats, so all 32 lanes work and an edge costs LDS.64 + 2 FADD), there is no second worker in the warp to
+// diverge from, and the row ends of the chunk sit in a register batch (one coalesced load, read by shuffle)
+// instead of being fetched one dependent load per row.  The per-row summation order is the chunk plan's, as
+// in A / C / T: the results are bit-identical.
+template <int VW> struct RV;
+template <> struct RV<2> {
+  typedef float2 T;
+  static __device__ __forceinline__ T lds(uint32_t a) {
+    T v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory"); return v;
+  }
+  static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a.x += b.x; a.y += b.y; }
+  static __device__ __forceinline__ void store(T* dst, T v, uint32_t deg, int epi) {
+    if (epi & ROC_SG_EPI_NORM) {
+      const RowDiv rd = rowdiv_make(sqrtf((float)deg));
+      float t[4] = {v.x, v.y, 0.f, 0.f};
+      rowdiv4(t, rd, 2);
+      v = make_float2(t[0], t[1]);
+    }
+    if (epi & ROC_SG_EPI_RELU) v = make_float2(relu_nanprop(v.x), relu_nanprop(v.y));
+    *dst = v;
+  }
+};
+template <> struct RV<4> {
+  typedef float4 T;
+  static __device__ __forceinline__ T lds(uint32_t a) { return lds128(a); }
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  static __device__ __forceinline__ void store(T* dst, T v, uint32_t deg, int epi) {
+    if (epi) epi_store<4>(v, dst, deg, epi); else *dst = v;
+  }
+};
+
+template <int VW, int NCH, int NPW, int MINB>
+__global__ void __launch_bounds__(32 * (NPW + 2), MINB)
+sg_ring_kernel(const SgParams p, const __grid_constant__ CUtensorMap tmap, uint32_t pairsPerCta) {
+  typedef typename RV<VW>::T T;
+  constexpr uint32_t CH = SG_CH;
+  constexpr uint32_t LANEB = VW * 4;                // bytes per lane per column block
+  constexpr uint32_t SLOTB = NCH * 32 * LANEB;      // shared-memory bytes per gathered row
+  constexpr uint32_t G4B = 4 * SLOTB;
+  constexpr uint32_t CHUNKB = CH * SLOTB;           // one slot
+  extern __shared__ __align__(128) unsigned char sg_smem_r[];
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sg_smem_r);
+  const uint32_t fullB = ring + 2 * CHUNKB, emptyB = fullB + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t numPairs = (p.numChunks + 1u) >> 1;
+  const uint32_t p0 = blockIdx.x * pairsPerCta;
+  if (p0 >= numPairs) return;
+  const uint32_t p1 = min(numPairs, p0 + pairsPerCta);
+  const uint32_t nIt = p1 - p0;
+  const uint32_t c0 = 2u * p0;
+  const uint32_t nLoaded = (p.E + CH - 1u) / CH;           // chunks that hold at least one edge
+  if (threadIdx.x == 0) {
+    mbar_init_a(fullB, 1); mbar_init_a(fullB + 8, 1);
+    mbar_init_a(emptyB, 2); mbar_init_a(emptyB + 8, 2);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp < NPW) {
+    // ----------------------------------------------------------- producers ---
+    // NPW warps share the 32 gather4s of a chunk pair: 32 / NPW lanes of each are active, lanes of one warp
+    // always serve the same slot (so the warp sees every phase of that slot's `empty` barrier).  One UTMALDG
+    // costs the issuing warp ~68 cycles (ELECT / R2UR loop), so a single warp needs ~2200 cycles per pair.
+    constexpr int PERW = 32 / NPW;                        // gather4s per producer warp and pair
+    const int g = warp * PERW + lane;                     // gather4 index within the pair: 0..15 slot 0, 16..31 slot 1
+    const int h = g >> 4, j = g & 15;
+    const bool mine = lane < PERW;
+    const uint32_t* __restrict__ col = p.col;
+    auto load_ids = [&](uint32_t c, uint4& v) {           // the four sources of gather4 #j of chunk c
+      const uint32_t e = c * CH + 4u * (uint32_t)j;
+      if (e + 4u <= p.E) {
+        v = __ldg(reinterpret_cast<const uint4*>(col + e));
+      } else if (e < p.E) {                                // the partial tail repeats the last edge's source
+        const uint32_t last = p.E - 1u;
+        v.x = __ldg(col + e); v.y = __ldg(col + min(e + 1u, last)); v.z = __ldg(col + min(e + 2u, last)); v.w = __ldg(col + min(e + 3u, last));
+      } else {
+        v = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (!mine) return;
+    uint4 nxt;
+    load_ids(c0 + (uint32_t)h, nxt);
+    // uses of slot h: it = 0 .. nIt-1, plus (h == 0 only) the chunk after the range, read by worker 1's tail
+    const uint32_t uses = nIt + (h == 0 ? 1u : 0u);
+#pragma unroll 1
+    for (uint32_t it = 0; it < uses; it++) {
+      const uint32_t c = c0 + 2u * it + (uint32_t)h;
+      const uint4 ids = nxt;
+      if (it + 1u < uses) load_ids(c + 2u, nxt);
+      if (c < nLoaded) {
+        const uint32_t nv = min(CH, p.E - c * CH);
+        const uint32_t n4 = (nv + 3u) >> 2;
+        mbar_wait_a(emptyB + 8u * h, (it & 1u) ^ 1u);
+        if (j == 0) mbar_expect_tx_a(fullB + 8u * h, n4 * G4B);
+        if ((uint32_t)j < n4) tma_gather4(ring + (uint32_t)h * CHUNKB + (uint32_t)j * G4B, &tmap, 0, ids.x, ids.y, ids.z, ids.w, fullB + 8u * h);
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- workers ---
+  const int h = warp - NPW;                                 // worker 0 / 1
+  const uint32_t* __restrict__ rs = p.rs;
+  const uint32_t validLanes = (p.Q * 16u + LANEB - 1u) / LANEB;      // lanes (per column block) that hold row data
+  bool act[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch++) act[ch] = (uint32_t)(lane + ch * 32) < validLanes;
+  if (h == 1) {
+    // Worker 1 first reads slot 0 at its SECOND use; it has to see the first one complete before it may wait
+    // for that (parity waits).  Its arrive stands in for the previous range's last worker, which reads its
+    // tail from its own CTA's copy of chunk c0.
+    if (c0 < nLoaded) mbar_wait_a(fullB, 0u);
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyB) : "memory");
+  }
+  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(p.desc);
+  uint4 d0, d1;
+  {
+    const uint32_t c = c0 + (uint32_t)h;
+    if (c < p.numChunks) { d0 = __ldg(descs + 2 * (size_t)c); d1 = __ldg(descs + 2 * (size_t)c + 1); }
+    else { d0 = make_uint4(0, 0, 0, 0); d1 = make_uint4(0, 0, 2u, 0); }
+  }
+  const uint32_t sa = ring + (uint32_t)lane * LANEB;
+  const size_t ldOutT = p.ldOut * 4 / VW, ldCT = p.ldC * 4 / VW;     // SgParams counts rows in float4 units
+
+#pragma unroll 1
+  for (uint32_t it = 0; it < nIt; it++) {
+    const uint32_t c = c0 + 2u * it + (uint32_t)h;
+    // this chunk's start state; the next one's record is requested now and used next iteration
+    const uint32_t eb = d0.x, ee = d0.y, r1 = d1.y, flags = d1.z, carrySlot = d1.w;
+    uint32_t cur = d0.z, curS = d0.w, curT = d1.x;
+    {
+      const uint32_t cn = c + 2u;
+      if (it + 1u < nIt && cn < p.numChunks) { d0 = __ldg(descs + 2 * (size_t)cn); d1 = __ldg(descs + 2 * (size_t)cn + 1); }
+      else { d0 = make_uint4(0, 0, 0, 0); d1 = make_uint4(0, 0, 2u, 0); }
+    }
+    const bool idle = (flags & 2u) != 0u || c >= p.numChunks;
+    const uint32_t ce = min(c * CH + CH, p.E);
+    int kind = (flags & 1u) ? 0 : ((curT - curS > CH) ? 2 : 1);
+    uint32_t segEnd = (kind == 1) ? curT : min(curT, ce);
+    const uint32_t boundary = (c + 1u) * CH;
+    // row ends of the rows after `cur`: lane i holds rs[rsBase + i] (clamped to the partition's last entry)
+    uint32_t rsBase = cur + 2u;
+    uint32_t rsReg = idle ? 0u : __ldg(rs + min(rsBase + (uint32_t)lane, p.nloc));
+
+    T acc[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) acc[ch] = RV<VW>::zero();
+    auto flush = [&]() {
+      T* dst = (kind == 0) ? reinterpret_cast<T*>(p.carry) + (size_t)carrySlot * ldCT
+                           : reinterpret_cast<T*>(p.out) + (size_t)cur * ldOutT;
+      dst += lane;
+      const int epi = (kind == 1) ? p.epi : 0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) {
+        if (act[ch]) RV<VW>::store(dst + ch * 32, acc[ch], curT - curS, epi);
+        acc[ch] = RV<VW>::zero();
+      }
+    };
+    auto advance = [&]() {
+      cur += 1; curS = curT;
+      const uint32_t k = cur + 1u - rsBase;                // rs[cur + 1] is entry k of the batch
+      if (k >= 32u) { rsBase = cur + 1u; rsReg = __ldg(rs + min(rsBase + (uint32_t)lane, p.nloc)); }
+      curT = __shfl_sync(0xffffffffu, rsReg, (int)((cur + 1u - rsBase) & 31u));
+      const bool heavy = curT - curS > CH;
+      segEnd = heavy ? min(curT, ce) : curT;
+      kind = heavy ? 2 : 1;
+    };
+
+    // phase 0: the worker's own chunk (slot h, use `it`); phase 1: its tail in the next chunk
+    // (slot h^1; for worker 1 that is slot 0's NEXT use)
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ph++) {
+      const uint32_t s = (uint32_t)(h ^ ph);
+      const uint32_t use = it + (uint32_t)(h & ph);
+      const uint32_t cc = c + (uint32_t)ph;
+      const bool loaded = cc < nLoaded;
+      if (loaded) mbar_wait_a(fullB + 8u * s, use & 1u);
+      const uint32_t eFrom = ph == 0 ? eb : max(eb, boundary);
+      const uint32_t eTo = ph == 0 ? min(ee, boundary) : ee;
+      if (!idle && eFrom < eTo) {
+#pragma unroll 1
+        for (uint32_t e0 = eFrom & ~3u; e0 < eTo; e0 += 4u) {
+          const uint32_t lo = max(eFrom, e0) - e0;
+          const uint32_t hi = min(eTo, e0 + 4u) - e0;
+          const uint32_t a = sa + (e0 & 127u) * SLOTB;
+          if (lo == 0u && hi == 4u && segEnd - e0 >= 4u) {
+            T v[4][NCH];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int ch = 0; ch < NCH; ch++) v[u][ch] = RV<VW>::lds(a + u * SLOTB + ch * 32 * LANEB);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int ch = 0; ch < NCH; ch++) RV<VW>::add(acc[ch], v[u][ch]);
+          } else {
+            uint32_t pos = lo;
+            for (;;) {
+              const uint32_t lim = min(hi, segEnd - e0);
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                if ((uint32_t)u >= pos && (uint32_t)u < lim) {
+#pragma unroll
+                  for (int ch = 0; ch < NCH; ch++) RV<VW>::add(acc[ch], RV<VW>::lds(a + u * SLOTB + ch * 32 * LANEB));
+                }
+              }
+              pos = max(pos, lim);
+              if (pos >= hi) break;
+              flush();
+              advance();
+            }
+          }
+        }
+      }
+      if (loaded) {
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyB + 8u * s) : "memory");
+      }
+    }
+    if (!idle) {
+      flush();
+      while (cur + 1 < r1) { advance(); flush(); }
+    }
+  }
+}
+
 // ----------------------------------------------------------- fix-up kernel ---
 // One worker per heavy row: out[R] = epilogue(out[R] + sum_k carry[slot0 + k]), k ascending.
 template <int VEC, int L, int NCH, int U>
@@ -844,10 +1120,10 @@ sg_fixup_big_kernel(const SgParams p) {
 // Variant A keeps the gathers in registers, variant C stages them in shared memory with
 // cp.async; C wins once a row needs two or more float4 per lane at L = 32 (H > 128).
 // ROC_SG_VARIANT=a|c forces one (experiments / cross-checks).
-static int sg_variant_env() {   // -1 default, 0 = A, 2 = C, 3 = T (TMA gather4), 4 = T with per-row bulk copies
+static int sg_variant_env() {   // -1 default, 0 = A, 2 = C, 3 = T (TMA gather4), 4 = T with per-row bulk copies, 5 = R (ring)
   const char* e = getenv("ROC_SG_VARIANT");   // re-read per call: the kernel bench switches it in-process
   if (!e) return -1;
-  switch (e[0]) { case 'a': return 0; case 'c': return 2; case 't': return 3; case 'b': return 4; default: return -1; }
+  switch (e[0]) { case 'a': return 0; case 'c': return 2; case 't': return 3; case 'b': return 4; case 'r': return 5; default: return -1; }
 }
 static int sg_deep_env() {   // ROC_SG_DEEP=1: variant C with a 2x deeper ring (experiments)
   const char* e = getenv("ROC_SG_DEEP");
@@ -887,6 +1163,47 @@ static cudaError_t launch_t(const SgParams& p, const CUtensorMap& tm, cudaStream
   return cudaGetLastError();
 }
 
+// ---- variant R launcher: NPW producer warps + two worker warps per CTA, MINB CTAs per SM
+template <int VW, int NCH, int NPW, int MINB>
+static cudaError_t launch_r(const SgParams& p, const CUtensorMap& tm, cudaStream_t st) {
+  constexpr size_t smem = (size_t)2 * SG_CH * NCH * 32 * VW * 4 + 64;
+  static_assert(smem * MINB <= 227 * 1024, "ring too large");
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = once_per_device(configured, [] {
+    return cudaFuncSetAttribute(sg_ring_kernel<VW, NCH, NPW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (e != cudaSuccess) return e;
+  const uint32_t numPairs = (p.numChunks + 1u) >> 1;
+  uint32_t grid = (uint32_t)sm_count() * MINB * 2u;        // two CTA ranges per resident slot
+  if (grid > numPairs) grid = numPairs;
+  const uint32_t per = (numPairs + grid - 1) / grid;
+  grid = (numPairs + per - 1) / per;
+  sg_ring_kernel<VW, NCH, NPW, MINB><<<grid, 32 * (NPW + 2), smem, st>>>(p, tm, per);
+  return cudaGetLastError();
+}
+// rows of up to 256 / 512 / 1024 bytes: 32 / 64 / 128 KB of ring per CTA.  cfg = producer warps (experiments)
+static cudaError_t launch_r_cfg(const SgParams& p, const CUtensorMap& tm, int cfg, cudaStream_t st) {
+  if (p.Q <= 16) {
+    switch (cfg) {
+      case 1: return launch_r<2, 1, 1, 6>(p, tm, st);
+      case 4: return launch_r<2, 1, 4, 6>(p, tm, st);
+      default: return launch_r<2, 1, 2, 6>(p, tm, st);
+    }
+  }
+  if (p.Q <= 32) {
+    switch (cfg) {
+      case 1: return launch_r<4, 1, 1, 3>(p, tm, st);
+      case 4: return launch_r<4, 1, 4, 3>(p, tm, st);
+      default: return launch_r<4, 1, 2, 3>(p, tm, st);
+    }
+  }
+  switch (cfg) {
+    case 1: return launch_r<4, 2, 1, 1>(p, tm, st);
+    case 4: return launch_r<4, 2, 4, 1>(p, tm, st);
+    default: return launch_r<4, 2, 2, 1>(p, tm, st);
+  }
+}
+
 // Ring shapes.  cfg < 0: the default for this width (chosen by measurement).
 template <int L, int NCH, int MODE>
 static cudaError_t launch_t_cfg(const SgParams& p, const CUtensorMap& tm, int cfg, cudaStream_t st) {
@@ -908,12 +1225,12 @@ static cudaError_t launch_t_cfg(const SgParams& p, const CUtensorMap& tm, int cf
       case 3: return launch_t<L, NCH, 1, 3, 128, 8, MODE>(p, tm, st);
       default: return launch_t<L, NCH, 1, 4, 128, 6, MODE>(p, tm, st);
     }
-  } else {                                 // 1 KB rows
+  } else {                                 // 1 KB rows: two 4 KB stages per warp, 6 CTAs (7.08 ms vs 8.34 with 4 stages x 3 CTAs)
     switch (cfg) {
-      case 1: return launch_t<L, NCH, 1, 2, 128, 6, MODE>(p, tm, st);
+      case 1: return launch_t<L, NCH, 1, 4, 128, 3, MODE>(p, tm, st);
       case 2: return launch_t<L, NCH, 1, 6, 128, 2, MODE>(p, tm, st);
       case 3: return launch_t<L, NCH, 1, 3, 128, 4, MODE>(p, tm, st);
-      default: return launch_t<L, NCH, 1, 4, 128, 3, MODE>(p, tm, st);
+      default: return launch_t<L, NCH, 1, 2, 128, 6, MODE>(p, tm, st);
     }
   }
 }
@@ -941,6 +1258,14 @@ static int launch_cfg(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
     unsigned grid = (p.numChunks + WPB - 1) / WPB;
     int variant = how.variant;
     bool done = false;
+    if constexpr (VEC == 4 && NCH <= 2 && L >= 16) {
+      if (variant == 5) {
+        cudaError_t e = launch_r_cfg(p, *how.tmap, how.tcfg, st);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        done = true;
+      }
+    }
     if constexpr (VEC == 4 && NCH <= 2) {
       if (variant == 3 || variant == 4) {
         cudaError_t e = (variant == 3) ? launch_t_cfg<L, NCH, 0>(p, *how.tmap, how.tcfg, st)
@@ -993,8 +1318,11 @@ static int dispatch(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
 static int pick_variant(uint32_t Q, bool vec) {
   int v = sg_variant_env();
   if (!vec) return 0;
-  if (v < 0) v = (Q > 32) ? 2 : 0;
-  if ((v == 3 || v == 4) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
+  // measured on R-MAT-22 (r2 runs 2 / 6 / 8, ms at H = 64 / 128 / 256): A 1.91 / 3.55 / 7.9, C 2.65 / 4.40 / 7.8,
+  // T 2.11 / 3.61 / 7.08, R 2.43 / 4.5 / 15.3 -> registers up to 128 floats, the TMA ring for 129..256
+  if (v < 0) v = (Q > 64) ? 2 : (Q > 32 ? 3 : 0);
+  if ((v == 3 || v == 4 || v == 5) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
+  if (v == 5 && Q <= 8) v = 0;                            // the ring kernel wants rows of 9+ float4
   return v;
 }
 
@@ -1071,6 +1399,10 @@ extern "C" int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid
     count_launch(6);
     PL_CUDA(cudaMemcpyAsync(&pl->numCarries, pl->carryIdx + pl->numChunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PL_CUDA(cudaMemcpyAsync(&pl->numBig, dcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PL_CUDA(cudaMalloc(&pl->desc, sizeof(uint32_t) * 8 * (size_t)pl->numChunks));
+    k_chunk_desc<<<(pl->numChunks + T - 1) / T, T, 0, st>>>(pl->numChunks, pl->E, pl->rs, pl->firstRow, pl->carryIdx, pl->desc);
+    count_launch();
+    PL_CUDA(cudaGetLastError());
     PL_CUDA(cudaStreamSynchronize(st));
     if (pl->E) {
       // rows the input matrix must have (1 + largest source id): the extent of the TMA tensor map
@@ -1095,7 +1427,7 @@ done:
 
 extern "C" void roc_sg_plan_destroy(roc_sg_plan* pl) {
   if (!pl) return;
-  cudaFree(pl->rs); cudaFree(pl->firstRow); cudaFree(pl->carryIdx); cudaFree(pl->heavyRows); cudaFree(pl->bigRows); cudaFree(pl->carry);
+  cudaFree(pl->rs); cudaFree(pl->firstRow); cudaFree(pl->carryIdx); cudaFree(pl->heavyRows); cudaFree(pl->bigRows); cudaFree(pl->carry); cudaFree(pl->desc);
   delete pl;
 }
 
@@ -1122,8 +1454,8 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
   // column blocks: the widest kernel covers 256 T-columns (1024 floats vectorised, 256 scalar);
   // the TMA variants take 64 T-columns (a tensor-map box is at most 256 elements wide)
   int variant = pick_variant(vec ? ((uint32_t)H + 3) / 4 : (uint32_t)H, vec);
-  if ((variant == 3 || variant == 4) && H > 256 && sg_variant_env() < 0) variant = 2;
-  const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4) ? 256 : 1024);
+  if ((variant == 3 || variant == 4 || variant == 5) && H > 256 && sg_variant_env() < 0) variant = 2;
+  const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4 || variant == 5) ? 256 : 1024);
   {
     int need = H < blockCols ? H : blockCols;
     int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4);
@@ -1136,6 +1468,7 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
     p.col = pl->col; p.in = in + c0; p.out = out + c0; p.carry = pl->carry;
     p.E = pl->E; p.numChunks = pl->numChunks; p.numHeavy = pl->numHeavy; p.numBig = pl->numBig; p.epi = epilogue;
     p.dense = (pl->nloc > 0 && pl->E / pl->nloc >= (uint32_t)SG_CH) ? 1 : 0;
+    p.desc = pl->desc; p.nloc = pl->nloc;
     SgLaunch how;
     how.variant = variant; how.tcfg = sg_tcfg_env(); how.tmap = nullptr;
     CUtensorMap tm;
@@ -1145,7 +1478,8 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
     if (vec) {
       p.ldIn = (size_t)ldIn / 4; p.ldOut = (size_t)ldOut / 4; p.ldC = pl->carryLd / 4;
       p.Q = ((uint32_t)hb + 3) / 4;
-      if (variant == 3) {
+      if (variant == 5 && (!aligned16(pl->col) || p.Q <= 8)) how.variant = 0;   // producer reads col as uint4
+      if (variant == 3 || how.variant == 5) {
         // tensor map of the input: [inRows][Q*4] floats, rows ldIn floats apart; the box is the worker's
         // whole lane span (columns past Q*4 are zero-filled), one row per box — gather4 fetches four
         const uint32_t span = p.Q <= 4 ? 4u : p.Q <= 8 ? 8u : p.Q <= 16 ? 16u : p.Q <= 32 ? 32u : 64u;

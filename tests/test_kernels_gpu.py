@@ -65,9 +65,10 @@ def test_sg_planned_vs_oracle(kind, h):
 @pytest.mark.parametrize("kind", ["uniform", "rmat", "dense", "ragged", "single"])
 @pytest.mark.parametrize("h", [4, 16, 41, 64, 100, 128, 200, 256, 602])
 def test_sg_variants_are_bitwise_identical(kind, h, monkeypatch):
-    """The register (A), cp.async (C) and TMA gather4 / bulk-copy (T) kernels share the chunk plan and the
-    per-row summation order, so they must agree bit for bit — with every ring shape of variant T and with
-    the fused epilogue — and the TMA path must meet the oracle exactly like the others."""
+    """The register (A), cp.async (C), TMA gather4 / bulk-copy (T) and producer/consumer ring (R) kernels share
+    the chunk plan and the per-row summation order, so they must agree bit for bit — with every ring shape of
+    variant T, every CTA-range split of variant R and with the fused epilogue — and the TMA paths must meet
+    the oracle exactly like the others."""
     row_end, col = graph(kind)
     n = row_end.shape[0]
     x = np.random.RandomState(h).randn(n, h).astype(np.float32)
@@ -78,7 +79,7 @@ def test_sg_variants_are_bitwise_identical(kind, h, monkeypatch):
     base = plan.forward(xp).clone()
     base_e = plan.forward(xp, epilogue=_lib.SG_EPI_NORM | _lib.SG_EPI_RELU).clone()
     rel_close(base.cpu().numpy(), oracle.scatter_gather(0, n - 1, 0, row_end, col, x), what="A %s H=%d" % (kind, h))
-    for variant, cfgs in (("c", [None]), ("t", [None, 1, 2, 3, 4, 5, 6]), ("b", [None, 1, 3])):
+    for variant, cfgs in (("c", [None]), ("r", [None, 1, 4]), ("t", [None, 1, 2, 3, 4, 5, 6]), ("b", [None, 1, 3])):
         monkeypatch.setenv("ROC_SG_VARIANT", variant)
         for cfg in cfgs:
             if cfg is None:
