@@ -93,6 +93,8 @@ struct RuntimeImpl {
   int new_tensor(int64_t rows, int H, int64_t ld, bool isInt, bool isWeight);
   float* data(int region);   // allocates on first use, zero-filled
   float* grad(int region);
+  // append `halo` rows to the data / grad buffer of x (re-allocating and copying if it already exists)
+  void grow_halo(TensorImpl& x, bool grad, int64_t halo);
   TensorImpl& t(int region) { return tensors[(size_t)region]; }
   void ensure_gather(size_t floats);
   void ensure_lin_ws(size_t bytes);

@@ -202,9 +202,11 @@ bool Model::init(const Config& config) {
         if (!as<ScatterGather>(layers[l])) continue;
         TensorImpl& xin = rt->t(layers[l]->inputs[0].region);
         TensorImpl& xout = rt->t(layers[l]->outputs[0].region);
-        ROC_ASSERT(xin.data == nullptr && xout.grad == nullptr);   // lazily allocated: not touched yet
-        xin.haloData = myGraph.numHalo;
-        xout.haloGrad = myGraph.numHalo;
+        // Usually neither buffer exists yet (lazy allocation).  A tensor the script already filled — e.g. an
+        // SGC-style scatter_gather(input) after load_features / set_tensor, which the reference's script order
+        // (gnn.cc:72-74) allows — is re-homed with the halo rows behind its own.
+        rt->grow_halo(xin, /*grad=*/false, myGraph.numHalo);
+        rt->grow_halo(xout, /*grad=*/true, myGraph.numHalo);
       }
     }
   }
@@ -427,8 +429,14 @@ void Model::load_features(const Tensor& input, const std::string& prefix) {
       ROC_ASSERT(feat_cnt == inDim);
     }
     if (rt->myPart == 0) {
-      FILE* binFout = fopen(binFile.c_str(), "wb");
-      if (binFout) { fwrite(all.data(), sizeof(float), all.size(), binFout); fclose(binFout); }
+      // the cache appears atomically (tmp + rename): another rank or job that finds <prefix>.feats.bin can read it whole
+      const std::string tmpFile = binFile + ".tmp";
+      FILE* binFout = fopen(tmpFile.c_str(), "wb");
+      if (binFout) {
+        const bool ok = fwrite(all.data(), sizeof(float), all.size(), binFout) == all.size();
+        if (fclose(binFout) == 0 && ok) rename(tmpFile.c_str(), binFile.c_str());
+        else remove(tmpFile.c_str());
+      }
     }
     memcpy(buf.data(), all.data() + (size_t)myGraph.rowLeft * inDim, buf.size() * sizeof(float));
   } else {
@@ -800,12 +808,16 @@ void SoftmaxCrossEntropy::backward(const Model& model) {
   if (mode == MD_MODE_INFER && model.printMetrics) {
     roc_perf_metrics p = model.last_metrics();
     // softmax_kernel.cu:141-152 (printed once per partition, quirk Q20)
-    fprintf(stderr,
-            "\t[INFER][%d] train_loss: %.4lf  train_accuracy: %.2lf%%(%d/%d)  val_accuracy: %.2lf%%(%d/%d)  "
-            "test_accuracy: %.2lf%%(%d/%d)\n",
-            epoch_num, p.trainLoss, p.trainCorrect * 100.0f / p.trainAll, p.trainCorrect, p.trainAll,
-            p.valCorrect * 100.0f / p.valAll, p.valCorrect, p.valAll, p.testCorrect * 100.0f / p.testAll,
-            p.testCorrect, p.testAll);
+    // to stderr AND stdout, as the reference does (scripts scrape either)
+    FILE* sinks[2] = {stderr, stdout};
+    for (FILE* f : sinks)
+      fprintf(f,
+              "\t[INFER][%d] train_loss: %.4lf  train_accuracy: %.2lf%%(%d/%d)  val_accuracy: %.2lf%%(%d/%d)  "
+              "test_accuracy: %.2lf%%(%d/%d)\n",
+              epoch_num, p.trainLoss, p.trainCorrect * 100.0f / p.trainAll, p.trainCorrect, p.trainAll,
+              p.valCorrect * 100.0f / p.valAll, p.valCorrect, p.valAll, p.testCorrect * 100.0f / p.testAll,
+              p.testCorrect, p.testAll);
+    fflush(stdout);
   }
 }
 

@@ -62,6 +62,21 @@ float* RuntimeImpl::grad(int region) {
   return x.grad;
 }
 
+void RuntimeImpl::grow_halo(TensorImpl& x, bool isGrad, int64_t halo) {
+  int64_t& have = isGrad ? x.haloGrad : x.haloData;
+  float*& buf = isGrad ? x.grad : x.data;
+  if (halo <= have) return;
+  if (buf) {
+    const size_t oldBytes = (size_t)(x.rows + have) * (size_t)x.ld * sizeof(float);
+    const size_t newBytes = (size_t)(x.rows + halo) * (size_t)x.ld * sizeof(float);
+    float* nb = (float*)dmalloc(newBytes);
+    ROC_CHECK(cudaMemsetAsync(nb, 0, newBytes, stream));
+    ROC_CHECK(cudaMemcpyAsync(nb, buf, oldBytes, cudaMemcpyDeviceToDevice, stream));
+    buf = nb;   // the old buffer stays in the arena until the Runtime goes away
+  }
+  have = halo;
+}
+
 void RuntimeImpl::ensure_gather(size_t floats) {
   if (floats <= gatherFloats) return;
   gatherBuf = (float*)dmalloc(floats * sizeof(float));   // old one stays in the arena (freed at exit)

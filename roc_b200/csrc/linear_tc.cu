@@ -439,9 +439,9 @@ k_tc_linear_ts(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   if (warp == 2) tmem_dealloc(tmemBase, p.tmemCols);
 }
 
-// scratch for the split weights (grow-only, per process; the host uses one stream)
-static float* g_wsplit = nullptr;
-static size_t g_wsplitFloats = 0;
+// The split weights (W_hi / W_lo, padded) live in a stream-ordered allocation made for this call
+// (cudaMallocAsync / cudaFreeAsync on the caller's stream): no process-wide scratch, so the C ABI can be driven
+// from several threads, devices and streams at once (the reference's task bodies run one per GPU in one process).
 
 struct TsEpilogue {
   int relu = 0;
@@ -466,13 +466,14 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   const int Npad = nTiles * BN;
   const int Kpad = (K + TC_BK - 1) / TC_BK * TC_BK;
   const size_t need = (size_t)2 * Npad * Kpad;
-  if (need > g_wsplitFloats) {
-    if (g_wsplit) { ROC_CUDA(cudaDeviceSynchronize()); ROC_CUDA(cudaFree(g_wsplit)); g_wsplit = nullptr; g_wsplitFloats = 0; }
-    ROC_CUDA(cudaMalloc(&g_wsplit, need * sizeof(float)));
-    g_wsplitFloats = need;
-  }
-  float* Whi = g_wsplit;
-  float* Wlo = g_wsplit + (size_t)Npad * Kpad;
+  float* wsplit = nullptr;
+  ROC_CUDA(cudaMallocAsync((void**)&wsplit, need * sizeof(float), st));
+  struct FreeOnExit {   // returned to the pool in stream order, after the GEMM below (or at once on an early return)
+    float* p; cudaStream_t s;
+    ~FreeOnExit() { if (p) cudaFreeAsync(p, s); }
+  } wsplitGuard{wsplit, st};
+  float* Whi = wsplit;
+  float* Wlo = wsplit + (size_t)Npad * Kpad;
   k_split_w<<<(Npad * Kpad + 255) / 256, 256, 0, st>>>(N, K, Npad, Kpad, ldW, transposed, W, Whi, Wlo);
   ROC_LAUNCH_CHECK();
 
@@ -516,11 +517,8 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   const unsigned threads = TS_THREADS;
 #define ROC_TS_LAUNCH(E)                                                                                          \
   do {                                                                                                            \
-    static size_t configured = 0;                                                                                 \
-    if (smemBytes > configured) {                                                                                 \
-      ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_ts<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes)); \
-      configured = smemBytes;                                                                                     \
-    }                                                                                                             \
+    static DynSmemCache configured;                                                                               \
+    ROC_CUDA(ensure_dyn_smem(k_tc_linear_ts<E>, smemBytes, configured));                                          \
     k_tc_linear_ts<E><<<grid, threads, smemBytes, st>>>(mapA, mapWhi, mapWlo, q);                                 \
   } while (0)
   switch (epi) {   // the combinations the GCN path produces; anything else takes the generic kernel

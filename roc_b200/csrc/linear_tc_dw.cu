@@ -308,18 +308,12 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     dim3 gridTs((unsigned)q.splits, (unsigned)q.groups, 1);
     const unsigned threadsTs = 128 + 128 * t.splitGroups;
     if (q.KS == 64) {
-      static size_t configured64 = 0;
-      if (smemTs > configured64) {
-        ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_dw_ts<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemTs));
-        configured64 = smemTs;
-      }
+      static DynSmemCache configured64;
+      ROC_CUDA(ensure_dyn_smem(k_tc_linear_dw_ts<64>, smemTs, configured64));
       k_tc_linear_dw_ts<64><<<gridTs, threadsTs, smemTs, st>>>(mapX, mapDY, mapM, t);
     } else {
-      static size_t configured16 = 0;
-      if (smemTs > configured16) {
-        ROC_CUDA(cudaFuncSetAttribute(k_tc_linear_dw_ts<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemTs));
-        configured16 = smemTs;
-      }
+      static DynSmemCache configured16;
+      ROC_CUDA(ensure_dyn_smem(k_tc_linear_dw_ts<16>, smemTs, configured16));
       k_tc_linear_dw_ts<16><<<gridTs, threadsTs, smemTs, st>>>(mapX, mapDY, mapM, t);
     }
     ROC_LAUNCH_CHECK();

@@ -1326,12 +1326,20 @@ static int pick_variant(uint32_t Q, bool vec) {
   return v;
 }
 
-static int ensure_carry(roc_sg_plan* plan, size_t ldFloats) {
+// Carry slots for rows cut at chunk boundaries.  roc_sg_plan_reserve sizes them up front (plain cudaMalloc, an
+// init-time call).  A launch that still finds them too small grows them on its own stream with stream-ordered
+// allocation: the old buffer is returned in stream order, after the launches that used it — no device
+// synchronisation in the middle of a step.
+static int ensure_carry(roc_sg_plan* plan, size_t ldFloats, cudaStream_t st, bool inStream) {
   if (plan->numCarries == 0 || ldFloats <= plan->carryLd) return ROC_OK;
-  if (plan->carry) { ROC_CUDA(cudaDeviceSynchronize()); ROC_CUDA(cudaFree(plan->carry)); plan->carry = nullptr; }
-  size_t bytes = (size_t)plan->numCarries * ldFloats * sizeof(float);
-  cudaError_t e = cudaMalloc(&plan->carry, bytes);
-  if (e != cudaSuccess) { plan->carryLd = 0; return (int)e; }
+  if (plan->carry) {
+    if (inStream) ROC_CUDA(cudaFreeAsync(plan->carry, st));
+    else { ROC_CUDA(cudaDeviceSynchronize()); ROC_CUDA(cudaFree(plan->carry)); }
+    plan->carry = nullptr; plan->carryLd = 0;
+  }
+  const size_t bytes = (size_t)plan->numCarries * ldFloats * sizeof(float);
+  cudaError_t e = inStream ? cudaMallocAsync((void**)&plan->carry, bytes, st) : cudaMalloc((void**)&plan->carry, bytes);
+  if (e != cudaSuccess) { plan->carry = nullptr; plan->carryLd = 0; return (int)e; }
   plan->carryLd = ldFloats;
   return ROC_OK;
 }
@@ -1433,7 +1441,7 @@ extern "C" void roc_sg_plan_destroy(roc_sg_plan* pl) {
 
 extern "C" int roc_sg_plan_reserve(roc_sg_plan* pl, int maxH) {
   if (!pl || maxH <= 0) return ROC_ERR_INVALID;
-  return ensure_carry(pl, ((size_t)maxH + 3) / 4 * 4);
+  return ensure_carry(pl, ((size_t)maxH + 3) / 4 * 4, nullptr, false);
 }
 
 extern "C" int roc_sg_plan_info(const roc_sg_plan* pl, uint64_t* numChunks, uint64_t* numCarries,
@@ -1458,7 +1466,7 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
   const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4 || variant == 5) ? 256 : 1024);
   {
     int need = H < blockCols ? H : blockCols;
-    int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4);
+    int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4, st, true);
     if (rc != ROC_OK) return rc;
   }
   for (int c0 = 0; c0 < H; c0 += blockCols) {
