@@ -77,6 +77,11 @@ const char* roc_version(void);
 int roc_device_count(void);
 /* Total kernels this library has launched in this process (for bench's gpu_launches). */
 uint64_t roc_launch_count(void);
+/* Persistent / grid-stride kernels launched by the CALLING THREAD from now on size their grids for
+ * (SMs - numSMs), leaving SMs to work running beside them on another stream (the peer-write halo exchange:
+ * a tcgen05 GEMM CTA holds a whole SM, nothing co-resides with it).  0 restores full-chip grids.  Returns the
+ * previous reserve. */
+int roc_set_sm_reserve(int numSMs);
 
 /* ---------------------------------------------------------------- graph --- */
 
@@ -170,6 +175,17 @@ int roc_halo_recv_layout(uint32_t nHalo, const roc_vid_t* host_ids, int numParts
                          const roc_vid_t* host_vbounds, uint64_t* recvCounts, uint64_t* recvOffs);
 int roc_halo_send_layout(int numParts, int myPart, const int32_t* host_allCounts, uint64_t* sendCounts,
                          uint64_t* sendOffs, uint64_t* numSendRows);
+/* Fused pack + exchange over peer memory: row srcRows[j] of `src` is stored to
+ * host_peerBase[peer[j]] + dstRow[j] * ldDst — the halo slab of the partition that reads it, in ANOTHER GPU's
+ * memory (device pointers the caller mapped with cudaIpcOpenMemHandle; the stores travel over NVLink).  Replaces
+ * roc_pack_rows + the NCCL all-to-all-v of the staged rows (themselves the replacement of the reference's
+ * whole-region request, scattergather.cc:69-73).  srcRows / peer / dstRow are device arrays of nRows entries;
+ * host_peerBase is a HOST array of numPeers <= ROC_MAX_PEERS device pointers (entries never named by peer[] may be
+ * NULL).  The caller orders the consumer after every producer (a barrier across the partitions). */
+#define ROC_MAX_PEERS 16
+int roc_push_rows(int64_t nRows, int H, const roc_vid_t* srcRows, const uint8_t* peer, const roc_vid_t* dstRow,
+                  const float* src, int64_t ldSrc, float* const* host_peerBase, int numPeers, int64_t ldDst,
+                  roc_stream_t stream);
 /* dst[j][0:H] = src[rows[j]][0:H]: packs the rows another partition asked for into a send buffer. */
 int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const float* src, int64_t ldSrc,
                   float* dst, int64_t ldDst, roc_stream_t stream);
@@ -324,7 +340,12 @@ typedef struct roc_linear_bwd_args {
   const uint32_t* dropMask; int64_t ldMask; float dropRate;
   const float* dxReluOf; int64_t ldReluOf;
   const roc_eid_t* dxNormRowEnd; roc_eid_t colLeft;
+  int parts;   /* 0 = dW and dX (if non-NULL); ROC_LINEAR_BWD_ONLY_DX / _ONLY_DW compute one of them — the host
+                * computes dX in row blocks (each pushed to the partitions that read it while the next is computed)
+                * and dW, which nothing waits for, last.  Only with activation == NONE (no in-place relu backward). */
 } roc_linear_bwd_args;
+#define ROC_LINEAR_BWD_ONLY_DX 1
+#define ROC_LINEAR_BWD_ONLY_DW 2
 int roc_linear_bwd_fused(const roc_linear_bwd_args* args, roc_stream_t stream);
 
 /* ------------------------------------------------------------ optimizer --- */

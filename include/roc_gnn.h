@@ -108,6 +108,15 @@ struct Graph {  /* gnn.h:120-130; ctor = gnn.cc:751-872 (reads <file>.add_self_e
   std::vector<size_t> recvCounts, recvOffs, sendCounts, sendOffs;   /* rows, per peer partition */
   V_ID* d_sendRows;      /* local rows other partitions read, grouped by requester */
   size_t numSendRows;
+  /* Peer-write exchange (roc_push_rows): the same send list sorted by source row, each entry with the partition
+   * that reads it and its row in that partition's [own | halo] slab; cut into row blocks so that a producer
+   * (Linear, softmax) can push block k while it computes block k + 1. */
+  V_ID* d_pushRows;
+  unsigned char* d_pushPeer;
+  V_ID* d_pushDst;
+  std::vector<V_ID> pushBlockRow;       /* [blocks + 1] first local row of each block */
+  std::vector<size_t> pushBlockOff;     /* [blocks + 1] offsets into the sorted send list */
+  std::vector<E_ID> pushBlockColLeft;   /* [blocks] global END offset of the row before the block */
 private:
   void build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc);
 };

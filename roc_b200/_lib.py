@@ -28,7 +28,7 @@ class LinearBwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspaceBytes", C.c_size_t),
                 ("dropMask", C.c_void_p), ("ldMask", C.c_int64), ("dropRate", C.c_float),
                 ("dxReluOf", C.c_void_p), ("ldReluOf", C.c_int64),
-                ("dxNormRowEnd", C.c_void_p), ("colLeft", C.c_uint64)]
+                ("dxNormRowEnd", C.c_void_p), ("colLeft", C.c_uint64), ("parts", C.c_int)]
 
 
 class PerfMetrics(C.Structure):
@@ -63,6 +63,7 @@ PROTOTYPES = {
     "roc_version": (C.c_char_p, []),
     "roc_device_count": (i32, []),
     "roc_launch_count": (u64, []),
+    "roc_set_sm_reserve": (i32, [i32]),
     "roc_partition": (i32, [u32, u64, i32, vp, vp, vp, vp]),
     "roc_build_csr": (i32, [u32, u32, u64, vp, vp, vp, vp, vp, vp]),
     "roc_sg_plan_create": (i32, [u32, u32, u64, vp, vp, vp, C.POINTER(vp)]),
@@ -80,6 +81,7 @@ PROTOTYPES = {
     "roc_halo_recv_layout": (i32, [u32, vp, i32, i32, vp, vp, vp]),
     "roc_halo_send_layout": (i32, [i32, i32, vp, vp, vp, vp]),
     "roc_pack_rows": (i32, [i64, i32, vp, vp, i64, vp, i64, vp]),
+    "roc_push_rows": (i32, [i64, i32, vp, vp, vp, vp, i64, vp, i32, i64, vp]),
     "roc_indegree_norm": (i32, [u32, u32, u64, i32, vp, vp, i64, vp, i64, vp, vp]),
     "roc_activation_fwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp]),
     "roc_activation_bwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp, i64, i32, vp]),

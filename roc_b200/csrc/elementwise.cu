@@ -14,6 +14,10 @@ namespace roc {
 
 std::atomic<uint64_t> g_launches{0};
 
+// SMs a persistent / grid-stride launch sizes itself for: the device's count minus what the calling thread
+// reserved with roc_set_sm_reserve (so that a peer-write exchange running on another stream finds free SMs:
+// the tcgen05 GEMMs hold a whole SM's registers and shared memory per CTA, nothing can co-reside with them).
+static thread_local int t_smReserve = 0;
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -23,7 +27,8 @@ int sm_count() {
     if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
     n = p.multiProcessorCount > 0 ? p.multiProcessorCount : 148;
   }
-  return n;
+  const int avail = n - t_smReserve;
+  return avail > 8 ? avail : 8;
 }
 
 static inline unsigned ew_grid(int64_t work_items, int threads) {
@@ -542,6 +547,11 @@ extern "C" int roc_device_count(void) {
 }
 
 extern "C" uint64_t roc_launch_count(void) { return g_launches.load(); }
+extern "C" int roc_set_sm_reserve(int numSMs) {
+  const int prev = t_smReserve;
+  t_smReserve = numSMs > 0 ? numSMs : 0;
+  return prev;
+}
 
 extern "C" int roc_partition(roc_vid_t numNodes, roc_eid_t numEdges, int numParts,
                              const roc_eid_t* raw_rows, roc_vid_t* vb, roc_eid_t* eb, int* numRanges) {

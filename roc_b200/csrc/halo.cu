@@ -64,6 +64,31 @@ k_pack_rows(int64_t nRows, int Wq, const uint32_t* __restrict__ rows, const floa
   }
 }
 
+// Fused pack + exchange: row srcRows[j] of this partition goes straight into the halo slab of the partition
+// that reads it — peerBase[peer[j]] is that GPU's tensor (mapped through CUDA IPC; the stores travel over
+// NVLink), dstRow[j] the row's place in its slab.  No staging buffer, no NCCL copy kernel: one pass over the
+// rows at NVLink speed.  A warp writes whole 16-byte segments of consecutive columns (coalesced 256-byte rows).
+struct PeerBases { float* p[ROC_MAX_PEERS]; };
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_push_rows(int64_t nRows, int Wq, const uint32_t* __restrict__ rows, const uint8_t* __restrict__ peer,
+            const uint32_t* __restrict__ dstRow, const float* __restrict__ src, int64_t ldSrc, PeerBases bases,
+            int64_t ldDst) {
+  const int64_t total = nRows * (int64_t)Wq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / Wq;
+    const int c = (int)(i - j * Wq);
+    const int64_t r = rows[j];
+    float* dst = bases.p[peer[j]] + (int64_t)dstRow[j] * ldDst;
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(dst + 4 * c) = __ldg(reinterpret_cast<const float4*>(src + r * ldSrc + 4 * c));
+    else
+      dst[c] = src[r * ldSrc + c];
+  }
+  __threadfence_system();   // the rows are in the peers' memory before this kernel counts as finished
+}
+
 }  // namespace roc
 
 using namespace roc;
@@ -151,6 +176,28 @@ extern "C" int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const 
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   if (vec) k_pack_rows<4><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, rows, src, ldSrc, dst, ldDst);
   else k_pack_rows<1><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, rows, src, ldSrc, dst, ldDst);
+  ROC_LAUNCH_CHECK();
+  return ROC_OK;
+}
+
+extern "C" int roc_push_rows(int64_t nRows, int H, const roc_vid_t* srcRows, const uint8_t* peer, const roc_vid_t* dstRow,
+                             const float* src, int64_t ldSrc, float* const* host_peerBase, int numPeers, int64_t ldDst,
+                             roc_stream_t stream) {
+  if (nRows < 0 || H <= 0 || ldSrc < H || ldDst < H || numPeers < 1 || numPeers > ROC_MAX_PEERS) return ROC_ERR_INVALID;
+  if (nRows == 0) return ROC_OK;
+  if (!srcRows || !peer || !dstRow || !src || !host_peerBase) return ROC_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  PeerBases b;
+  bool vec = (ldSrc % 4 == 0) && (ldDst % 4 == 0) && aligned16(src);
+  for (int q = 0; q < ROC_MAX_PEERS; q++) {
+    b.p[q] = q < numPeers ? host_peerBase[q] : nullptr;
+    if (b.p[q] && !aligned16(b.p[q])) vec = false;
+  }
+  const int Wq = vec ? (H + 3) / 4 : H;
+  int64_t blocks = (nRows * Wq + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;    // NVLink-bound: leave SMs to the kernels it runs beside
+  if (vec) k_push_rows<4><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+  else k_push_rows<1><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }

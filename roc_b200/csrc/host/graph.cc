@@ -51,6 +51,7 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   plan = nullptr;
   halo = nullptr; numHalo = 0; d_sendRows = nullptr; numSendRows = 0;
+  d_pushRows = nullptr; d_pushPeer = nullptr; d_pushDst = nullptr;
   const char* he = getenv("ROC_B200_HALO");
   const bool useHalo = rt->numParts > 1 && rt->commReady && !(he && he[0] == '0');
   if (!useHalo) {
@@ -101,6 +102,53 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
     }
     if (numSendRows)
       ROC_CHECK(cudaMemcpyAsync(d_sendRows, rows.data(), numSendRows * sizeof(V_ID), cudaMemcpyHostToDevice, rt->stream));
+    ROC_CHECK(cudaStreamSynchronize(rt->stream));
+  }
+  // ---- peer-write exchange: where does each send row land in its reader's slab?
+  {
+    // every rank's recvOffs (where owner r's rows start inside rank q's halo): [q][r]
+    std::vector<int> myOffs((size_t)P), allOffs((size_t)P * P);
+    for (int q = 0; q < P; q++) myOffs[(size_t)q] = (int)recvOffs[(size_t)q];
+    ROC_CHECK(cudaMemcpyAsync(d_cnt, myOffs.data(), sizeof(int) * P, cudaMemcpyHostToDevice, rt->stream));
+    ROC_CHECK(rt->comm.allgather_i32(d_cnt, d_cnt + P, (size_t)P, rt->stream));
+    ROC_CHECK(cudaMemcpyAsync(allOffs.data(), d_cnt + P, sizeof(int) * (size_t)P * P, cudaMemcpyDeviceToHost, rt->stream));
+    std::vector<V_ID> rows(numSendRows ? numSendRows : 1);
+    if (numSendRows)
+      ROC_CHECK(cudaMemcpyAsync(rows.data(), d_sendRows, numSendRows * sizeof(V_ID), cudaMemcpyDeviceToHost, rt->stream));
+    ROC_CHECK(cudaStreamSynchronize(rt->stream));
+    struct Ent { V_ID row; V_ID dst; unsigned char peer; };
+    std::vector<Ent> ents(numSendRows);
+    for (int q = 0; q < P; q++) {
+      const V_ID nlocQ = vbounds[2 * q + 1] - vbounds[2 * q] + 1;
+      const V_ID slab0 = nlocQ + (V_ID)allOffs[(size_t)q * P + me];       // my rows' place in q's [own | halo] slab
+      for (size_t j = 0; j < sendCounts[(size_t)q]; j++) {
+        Ent& e = ents[sendOffs[(size_t)q] + j];
+        e.row = rows[sendOffs[(size_t)q] + j]; e.dst = slab0 + (V_ID)j; e.peer = (unsigned char)q;
+      }
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.row < b.row; });
+    std::vector<V_ID> hr(numSendRows ? numSendRows : 1), hd(numSendRows ? numSendRows : 1);
+    std::vector<unsigned char> hp(numSendRows ? numSendRows : 1);
+    for (size_t j = 0; j < numSendRows; j++) { hr[j] = ents[j].row; hd[j] = ents[j].dst; hp[j] = ents[j].peer; }
+    d_pushRows = (V_ID*)rt->dmalloc(hr.size() * sizeof(V_ID));
+    d_pushDst = (V_ID*)rt->dmalloc(hd.size() * sizeof(V_ID));
+    d_pushPeer = (unsigned char*)rt->dmalloc(hp.size());
+    ROC_CHECK(cudaMemcpyAsync(d_pushRows, hr.data(), hr.size() * sizeof(V_ID), cudaMemcpyHostToDevice, rt->stream));
+    ROC_CHECK(cudaMemcpyAsync(d_pushDst, hd.data(), hd.size() * sizeof(V_ID), cudaMemcpyHostToDevice, rt->stream));
+    ROC_CHECK(cudaMemcpyAsync(d_pushPeer, hp.data(), hp.size(), cudaMemcpyHostToDevice, rt->stream));
+    // row blocks (multiples of 128 rows: whole GEMM tiles) and the CSR offset in front of each
+    int K = 4;
+    if (const char* e = getenv("ROC_B200_PUSH_BLOCKS")) K = std::max(1, atoi(e));
+    size_t per = (nloc + (size_t)K - 1) / (size_t)K;
+    per = (per + 127) / 128 * 128;
+    pushBlockRow.clear(); pushBlockOff.clear(); pushBlockColLeft.clear();
+    for (size_t r = 0; r < nloc; r += per) pushBlockRow.push_back((V_ID)r);
+    pushBlockRow.push_back((V_ID)nloc);
+    const size_t nb = pushBlockRow.size() - 1;
+    for (size_t k = 0; k <= nb; k++)
+      pushBlockOff.push_back((size_t)(std::lower_bound(hr.begin(), hr.begin() + numSendRows, pushBlockRow[k]) - hr.begin()));
+    for (size_t k = 0; k < nb; k++)
+      pushBlockColLeft.push_back(pushBlockRow[k] == 0 ? colLeft : host_rowEnd[rowLeft + pushBlockRow[k] - 1]);
     ROC_CHECK(cudaStreamSynchronize(rt->stream));
   }
   fprintf(stderr, "[roc_b200] part %d/%d: halo %u rows (%.1f%% of the %u remote vertices), sends %zu rows\n", me, P,

@@ -40,6 +40,9 @@ struct TensorImpl {
   float* data = nullptr;  // lazily allocated (node tensors)
   float* grad = nullptr;
   int32_t* labelIdx = nullptr;   // compact labels when loaded through load_labels / set_labels
+  // peer-write halo exchange: this tensor's buffers on the other partitions' GPUs (CUDA IPC mappings, index = part)
+  std::vector<float*> peerData, peerGrad;
+  bool freshData = false, freshGrad = false;   // the producer already pushed this step's boundary rows
 };
 
 // NCCL through dlopen so the library has no link-time NCCL dependency and, inside
@@ -57,6 +60,7 @@ struct Comm {
   int allreduce_sum(float* buf, size_t count, cudaStream_t st);
   int allreduce_sum_i32(int* buf, size_t count, cudaStream_t st);
   int allgather_i32(const int* sendbuf, int* recvbuf, size_t countPerRank, cudaStream_t st);
+  int barrier(int* scratch, cudaStream_t st);   // one-int all-reduce: completes once every rank's stream got here
   // all-to-all-v by grouped ncclSend / ncclRecv (counts and offsets in elements; no self transfer)
   int alltoallv(const void* sendbuf, const std::vector<size_t>& sendCounts, const std::vector<size_t>& sendOffs,
                 void* recvbuf, const std::vector<size_t>& recvCounts, const std::vector<size_t>& recvOffs,
@@ -66,7 +70,12 @@ struct Comm {
 
 struct RuntimeImpl {
   int device = 0, myPart = 0, numParts = 1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the compute stream: every op enqueues here
+  cudaStream_t commStream = nullptr;   // peer-write pushes of the halo exchange run here, beside the producer
+  cudaEvent_t evProduced = nullptr, evPushed = nullptr;
+  bool p2p = false;                    // halo exchange by peer writes (else staged rows + NCCL all-to-all-v)
+  int pushSMs = 16;                    // SMs left free for the push kernel while a producer is pipelined with it
+  int* d_barrier = nullptr;
   std::vector<TensorImpl> tensors;
   std::vector<void*> allocs;
   Comm comm;
@@ -95,6 +104,8 @@ struct RuntimeImpl {
   float* grad(int region);
   // append `halo` rows to the data / grad buffer of x (re-allocating and copying if it already exists)
   void grow_halo(TensorImpl& x, bool grad, int64_t halo);
+  // map the other partitions' copies of x's data / grad buffer (collective: every rank calls it for the same tensor)
+  bool open_peers(TensorImpl& x, bool grad);
   TensorImpl& t(int region) { return tensors[(size_t)region]; }
   void ensure_gather(size_t floats);
   void ensure_lin_ws(size_t bytes);

@@ -208,6 +208,24 @@ bool Model::init(const Config& config) {
         rt->grow_halo(xin, /*grad=*/false, myGraph.numHalo);
         rt->grow_halo(xout, /*grad=*/true, myGraph.numHalo);
       }
+      // Exchange by peer writes (roc_push_rows): the slabs exist now and every partition maps the others' copies.
+      // ROC_B200_HALO=nccl keeps the staged-rows + NCCL all-to-all-v exchange (cross-check; also the fallback when
+      // CUDA IPC is not available between the devices).
+      const char* he = getenv("ROC_B200_HALO");
+      rt->p2p = !(he && he[0] == 'n') && rt->numParts <= ROC_MAX_PEERS;
+      for (size_t l = 0; l < layers.size() && rt->p2p; l++) {
+        if (!as<ScatterGather>(layers[l])) continue;
+        const int rin = layers[l]->inputs[0].region, rout = layers[l]->outputs[0].region;
+        rt->data(rin);
+        if (!rt->open_peers(rt->t(rin), false)) { rt->p2p = false; break; }
+        if (rt->t(rin).requiresGrad) {
+          rt->grad(rout);
+          if (!rt->open_peers(rt->t(rout), true)) { rt->p2p = false; break; }
+        }
+      }
+      if (rt->myPart == 0)
+        fprintf(stderr, "[roc_b200] halo exchange: %s\n", rt->p2p ? "peer writes over NVLink (CUDA IPC), pipelined with the producer"
+                                                                  : "staged rows + NCCL all-to-all-v");
     }
   }
   // ---- fusion of  linear -> indegree_norm -> scatter_gather -> indegree_norm -> relu  (gnn.cc:81-85)
@@ -485,6 +503,44 @@ void Model::load_train_mask(const Tensor& mask, const std::string& prefix) {
   set_tensor(mask, m.data());
 }
 
+// ---- pipelined peer-write exchange: a producer computes its rows block by block and pushes block k's boundary
+// rows (commStream) while it computes block k + 1 (compute stream, on SMs - pushSMs)
+namespace {
+struct PushPipe {
+  RuntimeImpl* rt; const Graph* g; TensorImpl* x; bool isGrad; bool on; int prevReserve;
+  // the tensor `region` (data or grad) is read by a ScatterGather through peer-mapped halo slabs?
+  PushPipe(const Model& model, int region, bool grad) : rt(model.ctx), g(&model.myGraph), x(nullptr), isGrad(grad), on(false), prevReserve(0) {
+    if (region < 0 || !rt->p2p || rt->numParts == 1) return;
+    x = &rt->t(region);
+    const std::vector<float*>& peers = grad ? x->peerGrad : x->peerData;
+    on = !peers.empty() && g->pushBlockRow.size() >= 2;
+    if (on) prevReserve = roc_set_sm_reserve(rt->pushSMs);
+  }
+  size_t blocks() const { return on ? g->pushBlockRow.size() - 1 : 1; }
+  int64_t row0(size_t k) const { return on ? (int64_t)g->pushBlockRow[k] : 0; }
+  int64_t rows(size_t k, int64_t all) const { return on ? (int64_t)g->pushBlockRow[k + 1] - (int64_t)g->pushBlockRow[k] : all; }
+  E_ID colLeft(size_t k) const { return on ? g->pushBlockColLeft[k] : g->colLeft; }
+  // block k of `local` has been enqueued on the compute stream
+  void pushed(size_t k, float* local, int64_t ld, int H) {
+    if (!on) return;
+    const size_t a = g->pushBlockOff[k], b = g->pushBlockOff[k + 1];
+    std::vector<float*>& peers = isGrad ? x->peerGrad : x->peerData;
+    ROC_CHECK(cudaEventRecord(rt->evProduced, rt->stream));
+    ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->evProduced, 0));
+    if (b > a)
+      ROC_CHECK(roc_push_rows((int64_t)(b - a), H, g->d_pushRows + a, g->d_pushPeer + a, g->d_pushDst + a, local, ld,
+                              peers.data(), rt->numParts, ld, rt->commStream));
+    if (k + 1 == blocks()) {
+      ROC_CHECK(cudaEventRecord(rt->evPushed, rt->commStream));
+      (isGrad ? x->freshGrad : x->freshData) = true;
+    }
+  }
+  // kernels enqueued after this may use the whole chip again
+  void done() { if (on) { roc_set_sm_reserve(prevReserve); on = false; } }
+  ~PushPipe() { done(); }
+};
+}  // namespace
+
 // -------------------------------------------------------- ScatterGather -----
 ScatterGather::ScatterGather(const Model& model, const Tensor& _input)
     : GnnOp(_input), epilogue(0), bwdEpilogue(0), fwdOut(-1), bwdOut(-1) {
@@ -505,11 +561,29 @@ namespace {
 // (roc_pack_rows), one grouped NCCL send/recv moves them, and they land right behind the
 // partition's own rows ([Nloc | halo] is what the remapped col indexes).  ROC_B200_HALO=0 keeps
 // the whole-matrix all-gather (the reference's semantics) for comparison.
-const float* gathered(const Model& model, float* local, int64_t ld, int H) {
+const float* gathered(const Model& model, float* local, int64_t ld, int H, TensorImpl* x, bool isGrad) {
   RuntimeImpl* rt = model.ctx;
   if (rt->numParts == 1) return local;
   ROC_ASSERT(rt->commReady);
   const Graph& g = model.myGraph;
+  if (g.halo && rt->p2p) {
+    // Peer writes: unless the producer already pushed its rows block by block (fresh), push them all now; then wait
+    // for the pushes and cross the barrier after which every partition's rows are in this partition's slab.
+    std::vector<float*>& peers = isGrad ? x->peerGrad : x->peerData;
+    bool& fresh = isGrad ? x->freshGrad : x->freshData;
+    ROC_ASSERT(!peers.empty());
+    if (!fresh) {
+      ROC_CHECK(cudaEventRecord(rt->evProduced, rt->stream));
+      ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->evProduced, 0));
+      ROC_CHECK(roc_push_rows((int64_t)g.numSendRows, H, g.d_pushRows, g.d_pushPeer, g.d_pushDst, local, ld,
+                              peers.data(), rt->numParts, ld, rt->commStream));
+      ROC_CHECK(cudaEventRecord(rt->evPushed, rt->commStream));
+    }
+    fresh = false;
+    ROC_CHECK(cudaStreamWaitEvent(rt->stream, rt->evPushed, 0));
+    ROC_CHECK(rt->comm.barrier(rt->d_barrier, rt->stream));
+    return local;
+  }
   if (g.halo) {
     const size_t uld = (size_t)ld;
     rt->ensure_sendbuf((g.numSendRows ? g.numSendRows : 1) * uld);
@@ -536,7 +610,7 @@ void ScatterGather::forward(const Model& model) {
   const int H = (int)inputs[0].dims[0];
   const int64_t ldIn = rt->t(inputs[0].region).ld;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
-  const float* src = gathered(model, rt->data(inputs[0].region), ldIn, H);
+  const float* src = gathered(model, rt->data(inputs[0].region), ldIn, H, &rt->t(inputs[0].region), false);
   float* dst = rt->data(outRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, dst, rt->t(outRegion).ld, epilogue, rt->stream));
@@ -551,7 +625,7 @@ void ScatterGather::backward(const Model& model) {
   const int64_t ld = rt->t(outputs[0].region).ld;
   const int dstRegion = bwdOut >= 0 ? bwdOut : inputs[0].region;
   // Forward and backward do exactly the same thing, on gradients (scattergather_kernel.cu:168-169)
-  const float* src = gathered(model, rt->grad(outputs[0].region), ld, H);
+  const float* src = gathered(model, rt->grad(outputs[0].region), ld, H, &rt->t(outputs[0].region), true);
   float* dst = rt->grad(dstRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, dst, rt->t(dstRegion).ld, bwdEpilogue, rt->stream));
@@ -628,22 +702,38 @@ void Linear::forward(const Model& model) {
   RuntimeImpl* rt = model.ctx;
   const Graph& g = model.myGraph;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
+  // If a ScatterGather on other GPUs reads this output (peer-mapped halo slabs), the rows are computed in blocks
+  // and block k's boundary rows travel while block k + 1 is computed; otherwise one block = all rows.
+  PushPipe pipe(model, outRegion, /*grad=*/false);
+  const int inDim = (int)weight.dims[0], outDim = (int)weight.dims[1];
+  float* Y = rt->data(outRegion);
+  const int64_t ldY = rt->t(outRegion).ld;
   if (dropOp >= 0) {
     // dropout -> linear: the mask is generated packed (1 bit / element) and applied while the GEMM
     // loads X, so the dropped copy of X is never materialised
     const FusedDrop f = fused_drop(model, dropOp);
     if (f.rate > 0.0f)
-      ROC_CHECK(roc_dropout_mask(model.local_rows(), (int)weight.dims[0], g.rowLeft, f.rate, f.key, rt->trainStep,
+      ROC_CHECK(roc_dropout_mask(model.local_rows(), inDim, g.rowLeft, f.rate, f.key, rt->trainStep,
                                  dropMask, dropLd, rt->stream));
-    ROC_CHECK(roc_linear_fwd_dropout(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1],
-                                     rt->data(f.inRegion), rt->t(f.inRegion).ld, rt->data(weight.region),
-                                     rt->data(outRegion), rt->t(outRegion).ld, (int)activation, flags, g.d_rowEnd,
-                                     g.colLeft, dropMask, dropLd, f.rate, rt->stream));
+    const float* X = rt->data(f.inRegion);
+    const int64_t ldX = rt->t(f.inRegion).ld;
+    for (size_t k = 0; k < pipe.blocks(); k++) {
+      const int64_t r0 = pipe.row0(k), nr = pipe.rows(k, model.local_rows());
+      ROC_CHECK(roc_linear_fwd_dropout(nr, inDim, outDim, X + r0 * ldX, ldX, rt->data(weight.region), Y + r0 * ldY, ldY,
+                                       (int)activation, flags, g.d_rowEnd + r0, pipe.colLeft(k), dropMask + r0 * dropLd,
+                                       dropLd, f.rate, rt->stream));
+      pipe.pushed(k, Y, ldY, outDim);
+    }
     return;
   }
-  ROC_CHECK(roc_linear_fwd(model.local_rows(), (int)weight.dims[0], (int)weight.dims[1], rt->data(inputs[0].region),
-                           rt->t(inputs[0].region).ld, rt->data(weight.region), rt->data(outRegion),
-                           rt->t(outRegion).ld, (int)activation, flags, g.d_rowEnd, g.colLeft, rt->stream));
+  const float* X = rt->data(inputs[0].region);
+  const int64_t ldX = rt->t(inputs[0].region).ld;
+  for (size_t k = 0; k < pipe.blocks(); k++) {
+    const int64_t r0 = pipe.row0(k), nr = pipe.rows(k, model.local_rows());
+    ROC_CHECK(roc_linear_fwd(nr, inDim, outDim, X + r0 * ldX, ldX, rt->data(weight.region), Y + r0 * ldY, ldY,
+                             (int)activation, flags, g.d_rowEnd + r0, pipe.colLeft(k), rt->stream));
+    pipe.pushed(k, Y, ldY, outDim);
+  }
 }
 
 void Linear::backward(const Model& model) {
@@ -676,6 +766,28 @@ void Linear::backward(const Model& model) {
   a.workspace = rt->linWs; a.workspaceBytes = rt->linWsBytes;
   if (a.dX && dxReluOf >= 0) { a.dxReluOf = rt->data(dxReluOf); a.ldReluOf = rt->t(dxReluOf).ld; }
   if (a.dX && dxNorm) { a.dxNormRowEnd = g.d_rowEnd; a.colLeft = g.colLeft; }
+  // dX feeds a ScatterGather backward on other GPUs (peer-mapped slabs): dX in row blocks, each pushed while the
+  // next is computed, then dW — which nothing downstream waits for — while the last rows travel.
+  PushPipe pipe(model, (a.dX && activation == AC_MODE_NONE) ? dxRegion : -1, /*grad=*/true);
+  if (pipe.on) {
+    for (size_t k = 0; k < pipe.blocks(); k++) {
+      const int64_t r0 = pipe.row0(k), nr = pipe.rows(k, model.local_rows());
+      roc_linear_bwd_args b = a;
+      b.parts = ROC_LINEAR_BWD_ONLY_DX;
+      b.rows = nr;
+      b.X = a.X + r0 * a.ldX;
+      b.dY = a.dY + r0 * a.ldDY;
+      b.dX = a.dX + r0 * a.ldDX;
+      if (a.dropMask) b.dropMask = a.dropMask + r0 * a.ldMask;
+      if (a.dxReluOf) b.dxReluOf = a.dxReluOf + r0 * a.ldReluOf;
+      if (a.dxNormRowEnd) { b.dxNormRowEnd = a.dxNormRowEnd + r0; b.colLeft = pipe.colLeft(k); }
+      ROC_CHECK(roc_linear_bwd_fused(&b, rt->stream));
+      pipe.pushed(k, a.dX, a.ldDX, a.inDim);
+    }
+    a.parts = ROC_LINEAR_BWD_ONLY_DW;
+    ROC_CHECK(roc_linear_bwd_fused(&a, rt->stream));
+    return;
+  }
   ROC_CHECK(roc_linear_bwd_fused(&a, rt->stream));
 }
 
@@ -792,10 +904,20 @@ void SoftmaxCrossEntropy::backward(const Model& model) {
     // the logits come from an InDegreeNorm: its backward (grad / sqrt(deg)) is applied here and the
     // result goes straight into the gradient the ScatterGather backward reads
     const Graph& g = model.myGraph;
-    ROC_CHECK(roc_softmax_xent_bwd_norm(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
-                                        lab.labelIdx ? NULL : rt->data(inputs[1].region), lab.labelIdx ? 0 : lab.ld,
-                                        lab.labelIdx, mask, rt->grad(gradOut), rt->t(gradOut).ld, g.d_rowEnd,
-                                        g.colLeft, rt->d_perf, rt->stream));
+    PushPipe pipe(model, mode == MD_MODE_TRAIN ? gradOut : -1, /*grad=*/true);
+    const float* Z = rt->data(inputs[0].region);
+    const int64_t ldZ = rt->t(inputs[0].region).ld;
+    const float* L = lab.labelIdx ? NULL : rt->data(inputs[1].region);
+    const int64_t ldL = lab.labelIdx ? 0 : lab.ld;
+    float* G = rt->grad(gradOut);
+    const int64_t ldG = rt->t(gradOut).ld;
+    for (size_t k = 0; k < pipe.blocks(); k++) {
+      const int64_t r0 = pipe.row0(k), nr = pipe.rows(k, model.local_rows());
+      ROC_CHECK(roc_softmax_xent_bwd_norm(nr, C, Z + r0 * ldZ, ldZ, L ? L + r0 * ldL : NULL, ldL,
+                                          lab.labelIdx ? lab.labelIdx + r0 : NULL, mask + r0, G + r0 * ldG, ldG,
+                                          g.d_rowEnd + r0, pipe.colLeft(k), rt->d_perf, rt->stream));
+      pipe.pushed(k, G, ldG, C);
+    }
   } else if (lab.labelIdx) {
     ROC_CHECK(roc_softmax_xent_bwd_idx(model.local_rows(), C, rt->data(inputs[0].region), rt->t(inputs[0].region).ld,
                                        lab.labelIdx, mask, rt->grad(inputs[0].region), rt->t(inputs[0].region).ld,

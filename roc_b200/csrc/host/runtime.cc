@@ -4,6 +4,7 @@
 // cudaSetDevice, one stream and plain device allocations that live as long as the Runtime.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
 #include <cstring>
 
 #include "host_internal.h"
@@ -75,6 +76,53 @@ void RuntimeImpl::grow_halo(TensorImpl& x, bool isGrad, int64_t halo) {
     buf = nb;   // the old buffer stays in the arena until the Runtime goes away
   }
   have = halo;
+}
+
+// Collective.  Every rank exports the buffer's CUDA IPC handle, the handles are all-gathered over NCCL and each
+// rank maps the other ranks' buffers; returns false (the caller falls back to the NCCL exchange) if a mapping fails.
+bool RuntimeImpl::open_peers(TensorImpl& x, bool isGrad) {
+  std::vector<float*>& peers = isGrad ? x.peerGrad : x.peerData;
+  if (!peers.empty()) return true;
+  float* mine = isGrad ? x.grad : x.data;
+  ROC_ASSERT(mine != nullptr);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+  if (!ok) { cudaGetLastError(); memset(&h, 0, sizeof(h)); }
+  const int P = numParts;
+  int* d_h = (int*)dmalloc(sizeof(int) * 17 * (size_t)(P + 1));
+  int hostMine[17];
+  memcpy(hostMine, &h, 64); hostMine[16] = ok;
+  std::vector<int> all((size_t)17 * P);
+  ROC_CHECK(cudaMemcpyAsync(d_h, hostMine, sizeof(hostMine), cudaMemcpyHostToDevice, stream));
+  ROC_CHECK(comm.allgather_i32(d_h, d_h + 17, 17, stream));
+  ROC_CHECK(cudaMemcpyAsync(all.data(), d_h + 17, sizeof(int) * 17 * (size_t)P, cudaMemcpyDeviceToHost, stream));
+  ROC_CHECK(cudaStreamSynchronize(stream));
+  bool good = true;
+  for (int q = 0; q < P; q++) good = good && all[(size_t)17 * q + 16] == 1;
+  std::vector<float*> mapped((size_t)P, nullptr);
+  if (good) {
+    for (int q = 0; q < P && good; q++) {
+      if (q == myPart) { mapped[(size_t)q] = mine; continue; }
+      cudaIpcMemHandle_t hq;
+      memcpy(&hq, &all[(size_t)17 * q], 64);
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; }
+      mapped[(size_t)q] = (float*)p;
+    }
+  }
+  // every rank must take the same path: agree on the outcome
+  int flag = good ? 0 : 1;
+  ROC_CHECK(cudaMemcpyAsync(d_h, &flag, sizeof(int), cudaMemcpyHostToDevice, stream));
+  ROC_CHECK(comm.allreduce_sum_i32(d_h, 1, stream));
+  ROC_CHECK(cudaMemcpyAsync(&flag, d_h, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  ROC_CHECK(cudaStreamSynchronize(stream));
+  if (flag != 0) {
+    for (int q = 0; q < P; q++) if (q != myPart && mapped[(size_t)q]) cudaIpcCloseMemHandle(mapped[(size_t)q]);
+    return false;
+  }
+  peers = mapped;
+  return true;
 }
 
 void RuntimeImpl::ensure_gather(size_t floats) {
@@ -214,6 +262,10 @@ int Comm::allgather_i32(const int* sendbuf, int* recvbuf, size_t countPerRank, c
   return g_nccl.AllGather(sendbuf, recvbuf, countPerRank, ncclInt32, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
 }
 
+int Comm::barrier(int* scratch, cudaStream_t st) {
+  return g_nccl.AllReduce(scratch, scratch, 1, ncclInt32, ncclSum, (ncclComm_t)comm, st) == ncclSuccess ? 0 : -1;
+}
+
 int Comm::alltoallv(const void* sendbuf, const std::vector<size_t>& sendCounts, const std::vector<size_t>& sendOffs,
                     void* recvbuf, const std::vector<size_t>& recvCounts, const std::vector<size_t>& recvOffs,
                     bool isFloat, cudaStream_t st) {
@@ -251,6 +303,12 @@ Runtime::Runtime(int device, int myPart, int numParts) {
     ROC_FATAL("roc_b200: no CUDA device visible - this engine has no CPU fallback");
   ROC_CHECK(cudaSetDevice(device));
   ROC_CHECK(cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking));
+  ROC_CHECK(cudaStreamCreateWithFlags(&impl->commStream, cudaStreamNonBlocking));
+  ROC_CHECK(cudaEventCreateWithFlags(&impl->evProduced, cudaEventDisableTiming));
+  ROC_CHECK(cudaEventCreateWithFlags(&impl->evPushed, cudaEventDisableTiming));
+  impl->d_barrier = (int*)impl->dmalloc(sizeof(int));
+  ROC_CHECK(cudaMemsetAsync(impl->d_barrier, 0, sizeof(int), impl->stream));
+  if (const char* e = getenv("ROC_B200_PUSH_SMS")) impl->pushSMs = std::max(0, atoi(e));
   impl->d_perf = (roc_perf_metrics*)impl->dmalloc(sizeof(roc_perf_metrics));
   ROC_CHECK(cudaMemsetAsync(impl->d_perf, 0, sizeof(roc_perf_metrics), impl->stream));
 }
@@ -259,8 +317,15 @@ Runtime::~Runtime() {
   if (!impl) return;
   cudaSetDevice(impl->device);
   cudaDeviceSynchronize();
+  for (TensorImpl& x : impl->tensors) {
+    for (size_t q = 0; q < x.peerData.size(); q++) if ((int)q != impl->myPart && x.peerData[q]) cudaIpcCloseMemHandle(x.peerData[q]);
+    for (size_t q = 0; q < x.peerGrad.size(); q++) if ((int)q != impl->myPart && x.peerGrad[q]) cudaIpcCloseMemHandle(x.peerGrad[q]);
+  }
   impl->comm.destroy();
   impl->dfree_all();
+  if (impl->evProduced) cudaEventDestroy(impl->evProduced);
+  if (impl->evPushed) cudaEventDestroy(impl->evPushed);
+  if (impl->commStream) cudaStreamDestroy(impl->commStream);
   if (impl->stream) cudaStreamDestroy(impl->stream);
   delete impl;
 }

@@ -92,7 +92,11 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
                            const float* Y, int64_t ldY, float* dY, int64_t ldDY, float* dW, float* dX,
                            int64_t ldDX, int activation, int accumulate_dX, void* workspace,
                            size_t workspaceBytes, const DropMask* dm, const float* dxReluOf, int64_t ldReluOf,
-                           const roc_eid_t* dxRowEnd, roc_eid_t colLeft, roc_stream_t stream) {
+                           const roc_eid_t* dxRowEnd, roc_eid_t colLeft, roc_stream_t stream, int parts = 0) {
+  if (parts != 0 && (activation != ROC_AC_MODE_NONE || (parts != ROC_LINEAR_BWD_ONLY_DX && parts != ROC_LINEAR_BWD_ONLY_DW)))
+    return ROC_ERR_INVALID;
+  if (parts == ROC_LINEAR_BWD_ONLY_DX && !dX) return ROC_ERR_INVALID;
+  if (parts == ROC_LINEAR_BWD_ONLY_DW) { dX = nullptr; dxReluOf = nullptr; dxRowEnd = nullptr; }
   if ((dxReluOf || dxRowEnd) && !dX) return ROC_ERR_INVALID;
   if (dxReluOf && ldReluOf < inDim) return ROC_ERR_INVALID;
   if (!X || !W || !dY || !dW || rows < 0 || inDim <= 0 || outDim <= 0 || ldX < inDim || ldDY < outDim)
@@ -107,12 +111,15 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
     if (rc != ROC_OK) return rc;
   }
   if (!workspace) return ROC_ERR_INVALID;
-  int rc = ROC_ERR_UNSUPPORTED;
-  if (!force_simt())
-    rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
-  if (rc == ROC_ERR_UNSUPPORTED)
-    rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
-  if (rc != ROC_OK) return rc;
+  int rc = ROC_OK;
+  if (parts != ROC_LINEAR_BWD_ONLY_DX) {
+    rc = ROC_ERR_UNSUPPORTED;
+    if (!force_simt())
+      rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
+    if (rc == ROC_ERR_UNSUPPORTED)
+      rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
+    if (rc != ROC_OK) return rc;
+  }
   if (dX) {
     rc = ROC_ERR_UNSUPPORTED;
     if (!force_simt())
@@ -157,5 +164,5 @@ extern "C" int roc_linear_bwd_fused(const roc_linear_bwd_args* a, roc_stream_t s
   }
   return linear_bwd_impl(a->rows, a->inDim, a->outDim, a->X, a->ldX, a->W, a->Y, a->ldY, a->dY, a->ldDY, a->dW,
                          a->dX, a->ldDX, a->activation, a->accumulate_dX, a->workspace, a->workspaceBytes, use,
-                         a->dxReluOf, a->ldReluOf, a->dxNormRowEnd, a->colLeft, stream);
+                         a->dxReluOf, a->ldReluOf, a->dxNormRowEnd, a->colLeft, stream, a->parts);
 }

@@ -1,7 +1,9 @@
-"""GPU suite, part 3 (needs >= 2 GPUs; skipped on a single-GPU box): the vertex-range
-partitioned engine — one process per GPU, the feature all-gather before every
-ScatterGather and the dW all-reduce over NCCL — must reproduce the single-partition
-oracle: logits of every partition, the summed dW, the weights after several steps."""
+"""GPU suite, part 3 (needs >= 2 GPUs; skipped where the box has fewer than the case wants): the vertex-range
+partitioned engine — one process per GPU, the halo exchange before every ScatterGather (peer writes over
+NVLink pipelined with the producer, or staged rows + NCCL with ROC_B200_HALO=nccl) and the dW all-reduce over
+NCCL — must reproduce the single-partition oracle at 2, 4 and 8 ranks: logits of every partition, the summed
+dW, the weights after several steps.  (bench.py --gpus N runs the same kind of check on the driver's N-GPU
+box and prints it as `parity_check`.)"""
 import os
 import sys
 
@@ -65,43 +67,56 @@ def _worker(rank, world, port, tmpdir, dropout):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("dropout", [0.0, 0.5])
-def test_two_gpu_training_matches_oracle(tmp_path, dropout):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_training_matches_oracle(tmp_path, world, dropout, halo, monkeypatch):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    if halo == "nccl" and (world != 2 or dropout != 0.5):
+        pytest.skip("the NCCL exchange is cross-checked once")
     import torch.multiprocessing as mp
     from oracle import oracle
     from roc_b200 import datasets
     from test_model_gpu import sync_relu_masks
-    port = 29700 + os.getpid() % 1000
-    mp.spawn(_worker, args=(2, port, str(tmp_path), dropout), nprocs=2, join=True)
-    r = [np.load(tmp_path / ("rank%d.npy" % k), allow_pickle=True)[0] for k in range(2)]
+    if halo == "nccl":
+        monkeypatch.setenv("ROC_B200_HALO", "nccl")
+    else:
+        monkeypatch.delenv("ROC_B200_HALO", raising=False)
+    port = 29700 + (os.getpid() * 3 + world) % 1000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), dropout), nprocs=world, join=True)
+    r = [np.load(tmp_path / ("rank%d.npy" % k), allow_pickle=True)[0] for k in range(world)]
     row_end, col, feats, labels, mask = _case()
     n = row_end.shape[0]
-    k, vb, _ = oracle.partition(row_end, 2)
-    assert k == 2 and (r[0]["rl"], r[0]["rr"]) == (int(vb[0, 0]), int(vb[0, 1]))      # bit-exact partition bounds
-    assert (r[1]["rl"], r[1]["rr"]) == (int(vb[1, 0]), int(vb[1, 1])) and r[1]["rr"] == n - 1
-    for a, b in zip(r[0]["w0"], r[1]["w0"]):
-        assert np.array_equal(a, b)                   # same srand seed -> identical Glorot weights on every rank
+    k, vb, _ = oracle.partition(row_end, world)
+    assert k == world
+    for q in range(world):
+        assert (r[q]["rl"], r[q]["rr"]) == (int(vb[q, 0]), int(vb[q, 1]))      # bit-exact partition bounds
+    assert r[world - 1]["rr"] == n - 1
+    for q in range(1, world):
+        for a, b in zip(r[0]["w0"], r[q]["w0"]):
+            assert np.array_equal(a, b)               # same srand seed -> identical Glorot weights on every rank
     o = oracle.GcnOracle(row_end, col, LAYERS, r[0]["w0"], lr=0.01, weight_decay=0.05, dropout=dropout)
     oh = datasets.onehot(labels, LAYERS[-1])
     for ep in range(EPOCHS):
         o.forward(feats, train=True)
-        masks = [np.concatenate([r[0]["relu"][ep][i], r[1]["relu"][ep][i]]) for i in range(len(r[0]["relu"][ep]))]
+        masks = [np.concatenate([r[q]["relu"][ep][i] for q in range(world)]) for i in range(len(r[0]["relu"][ep]))]
         sync_relu_masks(o, masks)
         if ep == 0:
-            rel_close(np.concatenate([r[0]["logits"], r[1]["logits"]]), o.logits, what="stitched logits")
+            rel_close(np.concatenate([r[q]["logits"] for q in range(world)]), o.logits, what="stitched logits")
         o.backward(oh, mask)
         if ep == 0:
             for p in range(len(o.dW)):
-                rel_close(r[0]["dW_local"][p] + r[1]["dW_local"][p], o.dW[p], rtol=2e-4, what="sum of dW replicas")
-                assert np.array_equal(r[0]["dW_reduced"][p], r[1]["dW_reduced"][p])   # all-reduce: same bits everywhere
+                rel_close(sum(r[q]["dW_local"][p] for q in range(world)), o.dW[p], rtol=2e-4, what="sum of dW replicas")
+                for q in range(1, world):
+                    assert np.array_equal(r[0]["dW_reduced"][p], r[q]["dW_reduced"][p])   # all-reduce: same bits everywhere
                 rel_close(r[0]["dW_reduced"][p], o.dW[p], rtol=2e-4, what="all-reduced dW")
-        tot = r[0]["perf"][ep]["trainAll"] + r[1]["perf"][ep]["trainAll"]
+        tot = sum(r[q]["perf"][ep]["trainAll"] for q in range(world))
         assert tot == o.perf["trainAll"]
-        loss = r[0]["perf"][ep]["trainLoss"] + r[1]["perf"][ep]["trainLoss"]
+        loss = sum(r[q]["perf"][ep]["trainLoss"] for q in range(world))
         assert abs(loss - o.perf["trainLoss"]) <= 2e-4 * abs(o.perf["trainLoss"])
         o.update()
     for p in range(len(o.W)):
-        assert np.array_equal(r[0]["w"][p], r[1]["w"][p])
+        for q in range(1, world):
+            assert np.array_equal(r[0]["w"][p], r[q]["w"][p])
         rel_close(r[0]["w"][p], o.W[p], rtol=1e-3, atol_scale=1e-4, what="W[%d] after %d epochs" % (p, EPOCHS))
