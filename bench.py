@@ -429,7 +429,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel: ScatterGather at the hidden width on this rank's partition
     eloc = info["colRight"] - info["colLeft"] + 1
     hsg = layers[1]
-    sgh = [t for (h, t) in sg_times if h == hsg]
+    sgh = [t for (h, t) in sg_times if h == hsg]   # (exchange entries carry negative widths)
     peak, peak_src = peaks()
     roof = None
     if sgh:
@@ -455,7 +455,11 @@ def run_ours(args, rank, local_rank, world):
                 # the algorithmic bytes are mostly neighbour-row gathers and most of those sectors hit in L2
                 # (hub rows), so `frac` can exceed 1; this one uses the ncu DRAM traffic of this (config, N)
                 "frac_dram": (traffic / (t_avg * 1e-3) / 1e9 / peak) if traffic else None}
+    # negative widths are the part of the halo exchange the compute stream had to wait for (N > 1)
+    exch_times = [(-h, t) for (h, t) in sg_times if h < 0]
+    sg_times = [(h, t) for (h, t) in sg_times if h > 0]
     sg_share = sum(t for _, t in sg_times) / ms_total if sg_times else None
+    exch_ms = sum(t for _, t in exch_times) / args.steps if exch_times else None
 
     # ---- side columns (rank 0, N = 1 only): CPU oracle + the reference's own kernel on this GPU
     cpu = None
@@ -495,7 +499,7 @@ def run_ours(args, rank, local_rank, world):
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu,
-                "sg_share_of_step": sg_share, "reference_kernel": refk,
+                "sg_share_of_step": sg_share, "exposed_exchange_ms_per_step": exch_ms, "reference_kernel": refk,
                 "train_loss": perf["trainLoss"], "plan": host.plan_info(), "parity_check": parity}
         print(json.dumps(line), flush=True)
     host.close()

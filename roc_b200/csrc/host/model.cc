@@ -610,7 +610,9 @@ void ScatterGather::forward(const Model& model) {
   const int H = (int)inputs[0].dims[0];
   const int64_t ldIn = rt->t(inputs[0].region).ld;
   const int outRegion = fwdOut >= 0 ? fwdOut : outputs[0].region;
+  rt->sg_begin(-H);          // negative width = the exposed part of the halo exchange (profile mode only)
   const float* src = gathered(model, rt->data(inputs[0].region), ldIn, H, &rt->t(inputs[0].region), false);
+  rt->sg_end();
   float* dst = rt->data(outRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ldIn, dst, rt->t(outRegion).ld, epilogue, rt->stream));
@@ -625,7 +627,9 @@ void ScatterGather::backward(const Model& model) {
   const int64_t ld = rt->t(outputs[0].region).ld;
   const int dstRegion = bwdOut >= 0 ? bwdOut : inputs[0].region;
   // Forward and backward do exactly the same thing, on gradients (scattergather_kernel.cu:168-169)
+  rt->sg_begin(-H);
   const float* src = gathered(model, rt->grad(outputs[0].region), ld, H, &rt->t(outputs[0].region), true);
+  rt->sg_end();
   float* dst = rt->grad(dstRegion);
   rt->sg_begin(H);
   ROC_CHECK(roc_sg_forward_planned(model.myGraph.plan, H, src, ld, dst, rt->t(dstRegion).ld, bwdEpilogue, rt->stream));
