@@ -175,17 +175,24 @@ int roc_halo_recv_layout(uint32_t nHalo, const roc_vid_t* host_ids, int numParts
                          const roc_vid_t* host_vbounds, uint64_t* recvCounts, uint64_t* recvOffs);
 int roc_halo_send_layout(int numParts, int myPart, const int32_t* host_allCounts, uint64_t* sendCounts,
                          uint64_t* sendOffs, uint64_t* numSendRows);
+/* roc_pack_rows for a subset: dst[sel[t]] = src[rows[sel[t]]] for t < nSel — the send-list entries of one row
+ * block, written to their places in the send buffer, so that the block can travel (copy engines, peer slabs) while
+ * the producer computes the next one. */
+int roc_pack_rows_at(int64_t nSel, int H, const roc_vid_t* sel, const roc_vid_t* rows, const float* src,
+                     int64_t ldSrc, float* dst, int64_t ldDst, roc_stream_t stream);
 /* Fused pack + exchange over peer memory: row srcRows[j] of `src` is stored to
  * host_peerBase[peer[j]] + dstRow[j] * ldDst — the halo slab of the partition that reads it, in ANOTHER GPU's
  * memory (device pointers the caller mapped with cudaIpcOpenMemHandle; the stores travel over NVLink).  Replaces
  * roc_pack_rows + the NCCL all-to-all-v of the staged rows (themselves the replacement of the reference's
  * whole-region request, scattergather.cc:69-73).  srcRows / peer / dstRow are device arrays of nRows entries;
  * host_peerBase is a HOST array of numPeers <= ROC_MAX_PEERS device pointers (entries never named by peer[] may be
- * NULL).  The caller orders the consumer after every producer (a barrier across the partitions). */
+ * NULL).  smLimit > 0 sizes the grid for that many SMs (the ones a producer running beside it left free, see
+ * roc_set_sm_reserve); 0 = whole chip.  The caller orders the consumer after every producer (a barrier across
+ * the partitions). */
 #define ROC_MAX_PEERS 16
 int roc_push_rows(int64_t nRows, int H, const roc_vid_t* srcRows, const uint8_t* peer, const roc_vid_t* dstRow,
                   const float* src, int64_t ldSrc, float* const* host_peerBase, int numPeers, int64_t ldDst,
-                  roc_stream_t stream);
+                  int smLimit, roc_stream_t stream);
 /* dst[j][0:H] = src[rows[j]][0:H]: packs the rows another partition asked for into a send buffer. */
 int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const float* src, int64_t ldSrc,
                   float* dst, int64_t ldDst, roc_stream_t stream);

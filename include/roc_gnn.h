@@ -117,6 +117,12 @@ struct Graph {  /* gnn.h:120-130; ctor = gnn.cc:751-872 (reads <file>.add_self_e
   std::vector<V_ID> pushBlockRow;       /* [blocks + 1] first local row of each block */
   std::vector<size_t> pushBlockOff;     /* [blocks + 1] offsets into the sorted send list */
   std::vector<E_ID> pushBlockColLeft;   /* [blocks] global END offset of the row before the block */
+  /* Copy-engine exchange: block k's entries of the requester-grouped send list (d_packSel[packBlockOff[k] ..]),
+   * and, per requester q, where block k starts inside q's contiguous run (packPeerOff[q * (blocks + 1) + k]). */
+  V_ID* d_packSel;
+  std::vector<size_t> packBlockOff;
+  std::vector<size_t> packPeerOff;
+  std::vector<V_ID> peerSlab0;          /* [parts] first row of this partition's rows in partition q's [own | halo] slab */
 private:
   void build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc);
 };

@@ -81,7 +81,8 @@ PROTOTYPES = {
     "roc_halo_recv_layout": (i32, [u32, vp, i32, i32, vp, vp, vp]),
     "roc_halo_send_layout": (i32, [i32, i32, vp, vp, vp, vp]),
     "roc_pack_rows": (i32, [i64, i32, vp, vp, i64, vp, i64, vp]),
-    "roc_push_rows": (i32, [i64, i32, vp, vp, vp, vp, i64, vp, i32, i64, vp]),
+    "roc_pack_rows_at": (i32, [i64, i32, vp, vp, vp, i64, vp, i64, vp]),
+    "roc_push_rows": (i32, [i64, i32, vp, vp, vp, vp, i64, vp, i32, i64, i32, vp]),
     "roc_indegree_norm": (i32, [u32, u32, u64, i32, vp, vp, i64, vp, i64, vp, vp]),
     "roc_activation_fwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp]),
     "roc_activation_bwd": (i32, [i64, i32, i32, vp, i64, vp, i64, vp, i64, i32, vp]),

@@ -64,27 +64,71 @@ k_pack_rows(int64_t nRows, int Wq, const uint32_t* __restrict__ rows, const floa
   }
 }
 
+// dst[sel[t]][0:H] = src[rows[sel[t]]][0:H]: packs a SUBSET of the send list (the rows of one row block) into their
+// places in the send buffer, so that block can travel while the producer computes the next one.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_pack_rows_at(int64_t nSel, int Wq, const uint32_t* __restrict__ sel, const uint32_t* __restrict__ rows,
+               const float* __restrict__ src, int64_t ldSrc, float* __restrict__ dst, int64_t ldDst) {
+  const int64_t total = nSel * (int64_t)Wq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / Wq;
+    const int c = (int)(i - t * Wq);
+    const int64_t j = sel[t];
+    const int64_t r = rows[j];
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(dst + j * ldDst + 4 * c) = __ldg(reinterpret_cast<const float4*>(src + r * ldSrc + 4 * c));
+    else
+      dst[j * ldDst + c] = src[r * ldSrc + c];
+  }
+}
+
 // Fused pack + exchange: row srcRows[j] of this partition goes straight into the halo slab of the partition
 // that reads it — peerBase[peer[j]] is that GPU's tensor (mapped through CUDA IPC; the stores travel over
 // NVLink), dstRow[j] the row's place in its slab.  No staging buffer, no NCCL copy kernel: one pass over the
 // rows at NVLink speed.  A warp writes whole 16-byte segments of consecutive columns (coalesced 256-byte rows).
 struct PeerBases { float* p[ROC_MAX_PEERS]; };
 
-template <int VEC>
+// LR lanes share a row (one float4 column each; rows wider than LR float4 take several passes); every thread keeps
+// U rows in flight — loads of the U row ids / destinations, then the U 16-byte loads, then the U peer stores — so
+// that the few SMs a pipelined producer leaves free still fill NVLink: with one row per thread and iteration the
+// kernel needs ~140 K threads in flight for 770 GB/s (3 us per dependent load -> load -> store chain).
+template <int VEC, int LR, int U>
 __global__ void __launch_bounds__(256)
 k_push_rows(int64_t nRows, int Wq, const uint32_t* __restrict__ rows, const uint8_t* __restrict__ peer,
             const uint32_t* __restrict__ dstRow, const float* __restrict__ src, int64_t ldSrc, PeerBases bases,
             int64_t ldDst) {
-  const int64_t total = nRows * (int64_t)Wq;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = i / Wq;
-    const int c = (int)(i - j * Wq);
-    const int64_t r = rows[j];
-    float* dst = bases.p[peer[j]] + (int64_t)dstRow[j] * ldDst;
-    if (VEC == 4)
-      *reinterpret_cast<float4*>(dst + 4 * c) = __ldg(reinterpret_cast<const float4*>(src + r * ldSrc + 4 * c));
-    else
-      dst[c] = src[r * ldSrc + c];
+  constexpr int RPB = 256 / LR;                 // rows per CTA and step
+  const int c0 = threadIdx.x % LR;
+  const int64_t slot = threadIdx.x / LR;
+  const int64_t stride = (int64_t)gridDim.x * RPB;
+  for (int64_t jb = blockIdx.x * (int64_t)RPB + slot; jb < nRows; jb += stride * U) {
+    int64_t r[U];
+    float* d[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t j = jb + (int64_t)u * stride;
+      const bool ok = j < nRows;
+      r[u] = ok ? (int64_t)rows[j] : -1;
+      d[u] = ok ? bases.p[peer[j]] + (int64_t)dstRow[j] * ldDst : nullptr;
+    }
+    for (int c = c0; c < Wq; c += LR) {
+      if (VEC == 4) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (r[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(src + r[u] * ldSrc + 4 * c));
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (r[u] >= 0) *reinterpret_cast<float4*>(d[u] + 4 * c) = v[u];
+      } else {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) if (r[u] >= 0) v[u] = __ldg(src + r[u] * ldSrc + c);
+#pragma unroll
+        for (int u = 0; u < U; u++) if (r[u] >= 0) d[u][c] = v[u];
+      }
+    }
   }
   __threadfence_system();   // the rows are in the peers' memory before this kernel counts as finished
 }
@@ -182,7 +226,7 @@ extern "C" int roc_pack_rows(int64_t nRows, int H, const roc_vid_t* rows, const 
 
 extern "C" int roc_push_rows(int64_t nRows, int H, const roc_vid_t* srcRows, const uint8_t* peer, const roc_vid_t* dstRow,
                              const float* src, int64_t ldSrc, float* const* host_peerBase, int numPeers, int64_t ldDst,
-                             roc_stream_t stream) {
+                             int smLimit, roc_stream_t stream) {
   if (nRows < 0 || H <= 0 || ldSrc < H || ldDst < H || numPeers < 1 || numPeers > ROC_MAX_PEERS) return ROC_ERR_INVALID;
   if (nRows == 0) return ROC_OK;
   if (!srcRows || !peer || !dstRow || !src || !host_peerBase) return ROC_ERR_INVALID;
@@ -194,10 +238,36 @@ extern "C" int roc_push_rows(int64_t nRows, int H, const roc_vid_t* srcRows, con
     if (b.p[q] && !aligned16(b.p[q])) vec = false;
   }
   const int Wq = vec ? (H + 3) / 4 : H;
-  int64_t blocks = (nRows * Wq + 255) / 256;
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;    // NVLink-bound: leave SMs to the kernels it runs beside
-  if (vec) k_push_rows<4><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
-  else k_push_rows<1><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+  // NVLink-bound.  Beside a pipelined producer the grid is what fits on the SMs that producer left free (its CTAs
+  // hold whole SMs; ours would only queue behind them, or, worse, take SMs first and keep its CTAs out).
+  const int lr = Wq <= 16 ? 16 : 32;
+  int64_t blocks = (nRows + (256 / lr) * 8 - 1) / ((256 / lr) * 8);
+  const int64_t cap = (int64_t)(smLimit > 0 ? smLimit : sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (vec) {
+    if (lr == 16) k_push_rows<4, 16, 8><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+    else k_push_rows<4, 32, 8><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+  } else {
+    if (lr == 16) k_push_rows<1, 16, 8><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+    else k_push_rows<1, 32, 8><<<(unsigned)blocks, 256, 0, st>>>(nRows, Wq, srcRows, peer, dstRow, src, ldSrc, b, ldDst);
+  }
+  ROC_LAUNCH_CHECK();
+  return ROC_OK;
+}
+
+extern "C" int roc_pack_rows_at(int64_t nSel, int H, const roc_vid_t* sel, const roc_vid_t* rows, const float* src,
+                                int64_t ldSrc, float* dst, int64_t ldDst, roc_stream_t stream) {
+  if (nSel < 0 || H <= 0 || ldSrc < H || ldDst < H) return ROC_ERR_INVALID;
+  if (nSel == 0) return ROC_OK;
+  if (!sel || !rows || !src || !dst) return ROC_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const bool vec = (ldSrc % 4 == 0) && (ldDst % 4 == 0) && aligned16(src) && aligned16(dst);
+  const int Wq = vec ? (H + 3) / 4 : H;
+  int64_t blocks = (nSel * Wq + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  if (vec) k_pack_rows_at<4><<<(unsigned)blocks, 256, 0, st>>>(nSel, Wq, sel, rows, src, ldSrc, dst, ldDst);
+  else k_pack_rows_at<1><<<(unsigned)blocks, 256, 0, st>>>(nSel, Wq, sel, rows, src, ldSrc, dst, ldDst);
   ROC_LAUNCH_CHECK();
   return ROC_OK;
 }

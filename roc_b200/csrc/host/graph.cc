@@ -51,7 +51,7 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   plan = nullptr;
   halo = nullptr; numHalo = 0; d_sendRows = nullptr; numSendRows = 0;
-  d_pushRows = nullptr; d_pushPeer = nullptr; d_pushDst = nullptr;
+  d_pushRows = nullptr; d_pushPeer = nullptr; d_pushDst = nullptr; d_packSel = nullptr;
   const char* he = getenv("ROC_B200_HALO");
   const bool useHalo = rt->numParts > 1 && rt->commReady && !(he && he[0] == '0');
   if (!useHalo) {
@@ -149,6 +149,33 @@ void Graph::build(Context ctx, const E_ID* host_rowEnd, const V_ID* slice_colSrc
       pushBlockOff.push_back((size_t)(std::lower_bound(hr.begin(), hr.begin() + numSendRows, pushBlockRow[k]) - hr.begin()));
     for (size_t k = 0; k < nb; k++)
       pushBlockColLeft.push_back(pushBlockRow[k] == 0 ? colLeft : host_rowEnd[rowLeft + pushBlockRow[k] - 1]);
+    // copy-engine exchange: the requester-grouped list, cut by row block
+    {
+      std::vector<V_ID> sel;
+      sel.reserve(numSendRows ? numSendRows : 1);
+      packBlockOff.assign(nb + 1, 0);
+      packPeerOff.assign((size_t)P * (nb + 1), 0);
+      peerSlab0.assign((size_t)P, 0);
+      for (int q = 0; q < P; q++) {
+        const V_ID nlocQ = vbounds[2 * q + 1] - vbounds[2 * q] + 1;
+        peerSlab0[(size_t)q] = nlocQ + (V_ID)allOffs[(size_t)q * P + me];
+        const V_ID* b = rows.data() + sendOffs[(size_t)q];
+        const V_ID* e = b + sendCounts[(size_t)q];
+        for (size_t k = 0; k <= nb; k++)
+          packPeerOff[(size_t)q * (nb + 1) + k] = sendOffs[(size_t)q] + (size_t)(std::lower_bound(b, e, pushBlockRow[k]) - b);
+      }
+      for (size_t k = 0; k < nb; k++) {
+        packBlockOff[k] = sel.size();
+        for (int q = 0; q < P; q++)
+          for (size_t j = packPeerOff[(size_t)q * (nb + 1) + k]; j < packPeerOff[(size_t)q * (nb + 1) + k + 1]; j++) sel.push_back((V_ID)j);
+      }
+      packBlockOff[nb] = sel.size();
+      ROC_ASSERT(sel.size() == numSendRows);
+      d_packSel = (V_ID*)rt->dmalloc((sel.size() ? sel.size() : 1) * sizeof(V_ID));
+      if (!sel.empty())
+        ROC_CHECK(cudaMemcpyAsync(d_packSel, sel.data(), sel.size() * sizeof(V_ID), cudaMemcpyHostToDevice, rt->stream));
+      ROC_CHECK(cudaStreamSynchronize(rt->stream));
+    }
     ROC_CHECK(cudaStreamSynchronize(rt->stream));
   }
   fprintf(stderr, "[roc_b200] part %d/%d: halo %u rows (%.1f%% of the %u remote vertices), sends %zu rows\n", me, P,

@@ -73,8 +73,14 @@ struct RuntimeImpl {
   cudaStream_t stream = nullptr;       // the compute stream: every op enqueues here
   cudaStream_t commStream = nullptr;   // peer-write pushes of the halo exchange run here, beside the producer
   cudaEvent_t evProduced = nullptr, evPushed = nullptr;
-  bool p2p = false;                    // halo exchange by peer writes (else staged rows + NCCL all-to-all-v)
+  bool p2p = false;                    // halo exchange into peer-mapped slabs (else staged rows + NCCL all-to-all-v)
+  bool p2pCopyEngines = true;          // ... by pack + cudaMemcpyAsync per peer (DMA engines, no SMs); false: roc_push_rows
+  std::vector<cudaStream_t> peerStreams;   // one per partition: the copies to different peers run on different engines
+  std::vector<cudaEvent_t> peerDone;       // last copy of the current exchange on that stream
+  cudaEvent_t evPacked = nullptr;
+  bool exchInFlight = false;           // copies of the previous exchange may still read the send buffer
   int pushSMs = 16;                    // SMs left free for the push kernel while a producer is pipelined with it
+  int pushGridSMs = -1;                // SMs the pipelined push kernel's grid is sized for (-1: pushSMs, 0: whole chip)
   int* d_barrier = nullptr;
   std::vector<TensorImpl> tensors;
   std::vector<void*> allocs;
@@ -96,6 +102,15 @@ struct RuntimeImpl {
   std::vector<SgTiming> sgTimings;
   void sg_begin(int H);
   void sg_end();
+  // ROC_B200_OPPROF=1: device time of every op's forward / backward on the compute stream, averaged over the
+  // steps and printed by rank 0 when the Runtime goes away (where does a step's time go at N GPUs?)
+  struct OpTiming { int layer; int dir; cudaEvent_t a, b; };
+  bool opProf = false;
+  std::vector<OpTiming> opTimings;
+  std::vector<std::string> opNames;
+  void op_begin(int layer, int dir);
+  void op_end();
+  void op_report();
 
   void* dmalloc(size_t bytes);
   void dfree_all();

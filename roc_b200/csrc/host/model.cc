@@ -213,6 +213,7 @@ bool Model::init(const Config& config) {
       // CUDA IPC is not available between the devices).
       const char* he = getenv("ROC_B200_HALO");
       rt->p2p = !(he && he[0] == 'n') && rt->numParts <= ROC_MAX_PEERS;
+      rt->p2pCopyEngines = !(he && he[0] == 'p');      // ROC_B200_HALO=push: the SM kernel roc_push_rows instead
       for (size_t l = 0; l < layers.size() && rt->p2p; l++) {
         if (!as<ScatterGather>(layers[l])) continue;
         const int rin = layers[l]->inputs[0].region, rout = layers[l]->outputs[0].region;
@@ -224,8 +225,10 @@ bool Model::init(const Config& config) {
         }
       }
       if (rt->myPart == 0)
-        fprintf(stderr, "[roc_b200] halo exchange: %s\n", rt->p2p ? "peer writes over NVLink (CUDA IPC), pipelined with the producer"
-                                                                  : "staged rows + NCCL all-to-all-v");
+        fprintf(stderr, "[roc_b200] halo exchange: %s\n",
+                !rt->p2p ? "staged rows + NCCL all-to-all-v"
+                : rt->p2pCopyEngines ? "pack + copy-engine writes into the peers' slabs (CUDA IPC over NVLink), pipelined with the producer"
+                                     : "roc_push_rows peer writes (CUDA IPC over NVLink), pipelined with the producer");
     }
   }
   // ---- fusion of  linear -> indegree_norm -> scatter_gather -> indegree_norm -> relu  (gnn.cc:81-85)
@@ -325,6 +328,14 @@ bool Model::init(const Config& config) {
     }
   }
   for (size_t l = 0; l < layers.size(); l++) layers[l]->init(*this);
+  rt->opNames.clear();
+  for (size_t l = 0; l < layers.size(); l++) {
+    const char* nm = as<ScatterGather>(layers[l]) ? "scatter_gather" : as<Linear>(layers[l]) ? "linear" :
+                     as<InDegreeNorm>(layers[l]) ? "indegree_norm" : as<Activation>(layers[l]) ? "activation" :
+                     as<Dropout>(layers[l]) ? "dropout" : as<Element>(layers[l]) ? "add" :
+                     as<SoftmaxCrossEntropy>(layers[l]) ? "softmax_cross_entropy" : "op";
+    rt->opNames.push_back(std::string(nm) + (layers[l]->fusedInto >= 0 ? " (fused)" : ""));
+  }
   ROC_CHECK(cudaStreamSynchronize(rt->stream));
   return true;
 }
@@ -332,7 +343,11 @@ bool Model::init(const Config& config) {
 // gnn.cc:696-700
 void Model::forward(void) {
   if (mode == MD_MODE_TRAIN) ctx->trainStep += 1;
-  for (size_t l = 0; l < layers.size(); l++) layers[l]->forward(*this);
+  for (size_t l = 0; l < layers.size(); l++) {
+    ctx->op_begin((int)l, 0);
+    layers[l]->forward(*this);
+    ctx->op_end();
+  }
 }
 
 // gnn.cc:702-716
@@ -349,19 +364,23 @@ void Model::backward(void) {
         layers[l]->resetInputGrads[i] = false;
       }
     }
+    ctx->op_begin(l, 1);
     layers[l]->backward(*this);
+    ctx->op_end();
   }
 }
 
 // gnn.cc:718-724 (+ the replica sum of optimizer_kernel.cu:88-94 as one all-reduce)
 void Model::update(void) {
   RuntimeImpl* rt = ctx;
+  rt->op_begin(-1, 2);
   optimizer->next();
   if (rt->numParts > 1 && rt->flatGradCount) {
     ROC_ASSERT(rt->commReady);
     ROC_CHECK(rt->comm.allreduce_sum(rt->flatGrad, rt->flatGradCount, rt->stream));
   }
   for (int p = (int)parameters.size() - 1; p >= 0; p--) optimizer->update(&parameters[p]);
+  rt->op_end();
 }
 
 // gnn.cc:726-739
@@ -503,6 +522,58 @@ void Model::load_train_mask(const Tensor& mask, const std::string& prefix) {
   set_tensor(mask, m.data());
 }
 
+namespace {
+// Entries [selA, selB) of the block-ordered selection (or the whole requester-grouped list when blockK < 0) go to
+// the peers: packed into the send buffer on commStream, then one DMA copy per peer on that peer's stream.
+void exchange_rows(RuntimeImpl* rt, const Graph& g, float* local, int64_t ld, int H, std::vector<float*>& peers,
+                   int blockK, bool last, int smLimit) {
+  const size_t nb = g.pushBlockRow.size() - 1;
+  const int P = rt->numParts, me = rt->myPart;
+  ROC_CHECK(cudaEventRecord(rt->evProduced, rt->stream));
+  ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->evProduced, 0));
+  if (!rt->p2pCopyEngines) {
+    const size_t a = blockK < 0 ? 0 : g.pushBlockOff[(size_t)blockK], b = blockK < 0 ? g.numSendRows : g.pushBlockOff[(size_t)blockK + 1];
+    if (b > a)
+      ROC_CHECK(roc_push_rows((int64_t)(b - a), H, g.d_pushRows + a, g.d_pushPeer + a, g.d_pushDst + a, local, ld,
+                              peers.data(), P, ld, smLimit, rt->commStream));
+    if (last) ROC_CHECK(cudaEventRecord(rt->evPushed, rt->commStream));
+    return;
+  }
+  const size_t uld = (size_t)ld;
+  rt->ensure_sendbuf((g.numSendRows ? g.numSendRows : 1) * uld);
+  if ((blockK <= 0) && rt->exchInFlight) {
+    // the previous exchange's copies read the send buffer: the first pack of this one waits for them
+    for (int q = 0; q < P; q++) if (q != me) ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->peerDone[(size_t)q], 0));
+  }
+  if (blockK < 0) ROC_CHECK(roc_pack_rows((int64_t)g.numSendRows, H, g.d_sendRows, local, ld, rt->sendBuf, ld, rt->commStream));
+  else ROC_CHECK(roc_pack_rows_at((int64_t)(g.packBlockOff[(size_t)blockK + 1] - g.packBlockOff[(size_t)blockK]), H,
+                                  g.d_packSel + g.packBlockOff[(size_t)blockK], g.d_sendRows, local, ld, rt->sendBuf, ld,
+                                  rt->commStream));
+  ROC_CHECK(cudaEventRecord(rt->evPacked, rt->commStream));
+  for (int q = 0; q < P; q++) {
+    if (q == me) continue;
+    const size_t j0 = blockK < 0 ? g.sendOffs[(size_t)q] : g.packPeerOff[(size_t)q * (nb + 1) + (size_t)blockK];
+    const size_t j1 = blockK < 0 ? g.sendOffs[(size_t)q] + g.sendCounts[(size_t)q] : g.packPeerOff[(size_t)q * (nb + 1) + (size_t)blockK + 1];
+    cudaStream_t ps = rt->peerStreams[(size_t)q];
+    if (j1 > j0) {
+      ROC_CHECK(cudaStreamWaitEvent(ps, rt->evPacked, 0));
+      float* dst = peers[(size_t)q] + ((size_t)g.peerSlab0[(size_t)q] + (j0 - g.sendOffs[(size_t)q])) * uld;
+      ROC_CHECK(cudaMemcpyAsync(dst, rt->sendBuf + j0 * uld, (j1 - j0) * uld * sizeof(float), cudaMemcpyDeviceToDevice, ps));
+    }
+    if (last) ROC_CHECK(cudaEventRecord(rt->peerDone[(size_t)q], ps));
+  }
+  if (last) rt->exchInFlight = true;
+}
+// the compute stream waits for this partition's outgoing rows, then crosses the barrier behind which every
+// partition's rows have landed here
+void exchange_wait(RuntimeImpl* rt) {
+  if (!rt->p2pCopyEngines) ROC_CHECK(cudaStreamWaitEvent(rt->stream, rt->evPushed, 0));
+  else
+    for (int q = 0; q < rt->numParts; q++) if (q != rt->myPart) ROC_CHECK(cudaStreamWaitEvent(rt->stream, rt->peerDone[(size_t)q], 0));
+  ROC_CHECK(rt->comm.barrier(rt->d_barrier, rt->stream));
+}
+}  // namespace
+
 // ---- pipelined peer-write exchange: a producer computes its rows block by block and pushes block k's boundary
 // rows (commStream) while it computes block k + 1 (compute stream, on SMs - pushSMs)
 namespace {
@@ -514,7 +585,7 @@ struct PushPipe {
     x = &rt->t(region);
     const std::vector<float*>& peers = grad ? x->peerGrad : x->peerData;
     on = !peers.empty() && g->pushBlockRow.size() >= 2;
-    if (on) prevReserve = roc_set_sm_reserve(rt->pushSMs);
+    if (on && !rt->p2pCopyEngines) prevReserve = roc_set_sm_reserve(rt->pushSMs);   // the push KERNEL needs free SMs; DMA copies do not
   }
   size_t blocks() const { return on ? g->pushBlockRow.size() - 1 : 1; }
   int64_t row0(size_t k) const { return on ? (int64_t)g->pushBlockRow[k] : 0; }
@@ -523,20 +594,13 @@ struct PushPipe {
   // block k of `local` has been enqueued on the compute stream
   void pushed(size_t k, float* local, int64_t ld, int H) {
     if (!on) return;
-    const size_t a = g->pushBlockOff[k], b = g->pushBlockOff[k + 1];
     std::vector<float*>& peers = isGrad ? x->peerGrad : x->peerData;
-    ROC_CHECK(cudaEventRecord(rt->evProduced, rt->stream));
-    ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->evProduced, 0));
-    if (b > a)
-      ROC_CHECK(roc_push_rows((int64_t)(b - a), H, g->d_pushRows + a, g->d_pushPeer + a, g->d_pushDst + a, local, ld,
-                              peers.data(), rt->numParts, ld, rt->commStream));
-    if (k + 1 == blocks()) {
-      ROC_CHECK(cudaEventRecord(rt->evPushed, rt->commStream));
-      (isGrad ? x->freshGrad : x->freshData) = true;
-    }
+    const bool last = k + 1 == blocks();
+    exchange_rows(rt, *g, local, ld, H, peers, (int)k, last, rt->pushGridSMs >= 0 ? rt->pushGridSMs : rt->pushSMs);
+    if (last) (isGrad ? x->freshGrad : x->freshData) = true;
   }
   // kernels enqueued after this may use the whole chip again
-  void done() { if (on) { roc_set_sm_reserve(prevReserve); on = false; } }
+  void done() { if (on) { if (!rt->p2pCopyEngines) roc_set_sm_reserve(prevReserve); on = false; } }
   ~PushPipe() { done(); }
 };
 }  // namespace
@@ -572,16 +636,9 @@ const float* gathered(const Model& model, float* local, int64_t ld, int H, Tenso
     std::vector<float*>& peers = isGrad ? x->peerGrad : x->peerData;
     bool& fresh = isGrad ? x->freshGrad : x->freshData;
     ROC_ASSERT(!peers.empty());
-    if (!fresh) {
-      ROC_CHECK(cudaEventRecord(rt->evProduced, rt->stream));
-      ROC_CHECK(cudaStreamWaitEvent(rt->commStream, rt->evProduced, 0));
-      ROC_CHECK(roc_push_rows((int64_t)g.numSendRows, H, g.d_pushRows, g.d_pushPeer, g.d_pushDst, local, ld,
-                              peers.data(), rt->numParts, ld, rt->commStream));
-      ROC_CHECK(cudaEventRecord(rt->evPushed, rt->commStream));
-    }
+    if (!fresh) exchange_rows(rt, g, local, ld, H, peers, /*blockK=*/-1, /*last=*/true, /*smLimit=*/0);
     fresh = false;
-    ROC_CHECK(cudaStreamWaitEvent(rt->stream, rt->evPushed, 0));
-    ROC_CHECK(rt->comm.barrier(rt->d_barrier, rt->stream));
+    exchange_wait(rt);
     return local;
   }
   if (g.halo) {

@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cstring>
+#include <map>
 
 #include "host_internal.h"
 
@@ -141,6 +142,40 @@ void RuntimeImpl::sg_begin(int H) {
 void RuntimeImpl::sg_end() {
   if (!profileSg || sgTimings.empty()) return;
   ROC_CHECK(cudaEventRecord(sgTimings.back().b, stream));
+}
+
+void RuntimeImpl::op_begin(int layer, int dir) {
+  if (!opProf) return;
+  OpTiming t; t.layer = layer; t.dir = dir;
+  ROC_CHECK(cudaEventCreate(&t.a)); ROC_CHECK(cudaEventCreate(&t.b));
+  ROC_CHECK(cudaEventRecord(t.a, stream));
+  opTimings.push_back(t);
+}
+void RuntimeImpl::op_end() {
+  if (!opProf || opTimings.empty()) return;
+  ROC_CHECK(cudaEventRecord(opTimings.back().b, stream));
+}
+void RuntimeImpl::op_report() {
+  if (!opProf || opTimings.empty()) return;
+  cudaDeviceSynchronize();
+  std::map<std::pair<int, int>, std::pair<double, int>> acc;
+  for (OpTiming& t : opTimings) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { auto& e = acc[{t.layer, t.dir}]; e.first += ms; e.second += 1; }
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  opTimings.clear();
+  if (myPart != 0) return;
+  double tot = 0;
+  fprintf(stderr, "[roc_b200] op profile (ms per call on the compute stream, part 0 of %d):\n", numParts);
+  for (auto& kv : acc) {
+    const double ms = kv.second.first / kv.second.second;
+    tot += ms;
+    const int l = kv.first.first;
+    fprintf(stderr, "  %-3s layer %2d %-22s %8.3f  (%d calls)\n", kv.first.second == 0 ? "fwd" : (kv.first.second == 1 ? "bwd" : "upd"), l,
+            (l >= 0 && (size_t)l < opNames.size()) ? opNames[(size_t)l].c_str() : "-", ms, kv.second.second);
+  }
+  fprintf(stderr, "  sum %8.3f ms\n", tot);
 }
 
 void RuntimeImpl::ensure_sendbuf(size_t floats) {
@@ -302,13 +337,32 @@ Runtime::Runtime(int device, int myPart, int numParts) {
   if (roc_device_count() <= 0)
     ROC_FATAL("roc_b200: no CUDA device visible - this engine has no CPU fallback");
   ROC_CHECK(cudaSetDevice(device));
-  ROC_CHECK(cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking));
-  ROC_CHECK(cudaStreamCreateWithFlags(&impl->commStream, cudaStreamNonBlocking));
+  {
+    // The compute stream outranks the exchange stream: when a producer block and the push of the previous block
+    // become runnable together, the producer's CTAs (a whole SM each) are placed first and the push kernel takes
+    // the SMs the producer left free — the other way round its small CTAs would sit on every SM and keep the
+    // producer out (r2 run m2: 29.0 ms/step at 8 GPUs although only 2.0 ms of the exchange were exposed).
+    int lo = 0, hi = 0;   // numerically lower = higher priority
+    ROC_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const char* pe = getenv("ROC_B200_PUSH_PRIO");          // experiments: 0 = equal priorities
+    const bool prio = !(pe && pe[0] == '0');
+    ROC_CHECK(cudaStreamCreateWithPriority(&impl->stream, cudaStreamNonBlocking, prio ? hi : lo));
+    ROC_CHECK(cudaStreamCreateWithPriority(&impl->commStream, cudaStreamNonBlocking, lo));
+  }
   ROC_CHECK(cudaEventCreateWithFlags(&impl->evProduced, cudaEventDisableTiming));
   ROC_CHECK(cudaEventCreateWithFlags(&impl->evPushed, cudaEventDisableTiming));
+  ROC_CHECK(cudaEventCreateWithFlags(&impl->evPacked, cudaEventDisableTiming));
+  for (int q = 0; q < numParts && numParts > 1; q++) {
+    cudaStream_t ps = nullptr; cudaEvent_t pe = nullptr;
+    ROC_CHECK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    ROC_CHECK(cudaEventCreateWithFlags(&pe, cudaEventDisableTiming));
+    impl->peerStreams.push_back(ps); impl->peerDone.push_back(pe);
+  }
   impl->d_barrier = (int*)impl->dmalloc(sizeof(int));
   ROC_CHECK(cudaMemsetAsync(impl->d_barrier, 0, sizeof(int), impl->stream));
   if (const char* e = getenv("ROC_B200_PUSH_SMS")) impl->pushSMs = std::max(0, atoi(e));
+  if (const char* e = getenv("ROC_B200_OPPROF")) impl->opProf = e[0] == '1';
+  if (const char* e = getenv("ROC_B200_PUSH_GRID")) impl->pushGridSMs = atoi(e);   // experiments: SMs the pipelined push grid is sized for (0 = chip)
   impl->d_perf = (roc_perf_metrics*)impl->dmalloc(sizeof(roc_perf_metrics));
   ROC_CHECK(cudaMemsetAsync(impl->d_perf, 0, sizeof(roc_perf_metrics), impl->stream));
 }
@@ -317,12 +371,16 @@ Runtime::~Runtime() {
   if (!impl) return;
   cudaSetDevice(impl->device);
   cudaDeviceSynchronize();
+  impl->op_report();
   for (TensorImpl& x : impl->tensors) {
     for (size_t q = 0; q < x.peerData.size(); q++) if ((int)q != impl->myPart && x.peerData[q]) cudaIpcCloseMemHandle(x.peerData[q]);
     for (size_t q = 0; q < x.peerGrad.size(); q++) if ((int)q != impl->myPart && x.peerGrad[q]) cudaIpcCloseMemHandle(x.peerGrad[q]);
   }
   impl->comm.destroy();
   impl->dfree_all();
+  for (cudaStream_t ps : impl->peerStreams) cudaStreamDestroy(ps);
+  for (cudaEvent_t pe : impl->peerDone) cudaEventDestroy(pe);
+  if (impl->evPacked) cudaEventDestroy(impl->evPacked);
   if (impl->evProduced) cudaEventDestroy(impl->evProduced);
   if (impl->evPushed) cudaEventDestroy(impl->evPushed);
   if (impl->commStream) cudaStreamDestroy(impl->commStream);
