@@ -213,7 +213,11 @@ bool Model::init(const Config& config) {
       // CUDA IPC is not available between the devices).
       const char* he = getenv("ROC_B200_HALO");
       rt->p2p = !(he && he[0] == 'n') && rt->numParts <= ROC_MAX_PEERS;
-      rt->p2pCopyEngines = !(he && he[0] == 'p');      // ROC_B200_HALO=push: the SM kernel roc_push_rows instead
+      // Two ways to fill the peers' slabs, chosen by measurement (r2 runs m5-m8, ms/step at 2 / 4 / 8 GPUs):
+      // pack + one DMA copy per peer 20.8 / - / 33.1 (the copy engines do not keep 7 peer copies busy), the SM
+      // kernel roc_push_rows 21.2 / 24.8 / 29.0, staged rows + NCCL 21.8 / 26.0 / 30.7.
+      // ROC_B200_HALO=push | ce forces one.
+      rt->p2pCopyEngines = (he && he[0] == 'c') ? true : (he && he[0] == 'p') ? false : rt->numParts == 2;
       for (size_t l = 0; l < layers.size() && rt->p2p; l++) {
         if (!as<ScatterGather>(layers[l])) continue;
         const int rin = layers[l]->inputs[0].region, rout = layers[l]->outputs[0].region;
