@@ -38,8 +38,16 @@ $(BIN): $(BUILD)/host_main.o $(LIB)
 oracle:
 	$(MAKE) -C oracle all
 
+# compute-sanitizer (memcheck + racecheck) over the tiny configuration; needs a GPU
+sanitize: $(LIB)
+	tools/sanitize.sh
+
+# the gather-ceiling measurement tool (what can a B200 deliver for random row gathers?)
+tools/gather_ceiling: tools/gather_ceiling.cu
+	$(NVCC) $(ARCH) -O3 -o $@ $<
+
 clean:
 	rm -rf $(BUILD) $(LIB) $(BIN)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean sanitize

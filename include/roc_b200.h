@@ -355,6 +355,13 @@ typedef struct roc_linear_bwd_args {
 #define ROC_LINEAR_BWD_ONLY_DW 2
 int roc_linear_bwd_fused(const roc_linear_bwd_args* args, roc_stream_t stream);
 
+/* Test hook: which kernel family served the calling thread's last Linear GEMM — which = 0 forward, 1 dW, 2 dX;
+ * returns ROC_GEMM_PATH_TCGEN05, ROC_GEMM_PATH_SIMT (the exact-fp32 fallback for shapes / alignments the tensor-core
+ * kernels do not take) or 0 (none yet). */
+#define ROC_GEMM_PATH_TCGEN05 1
+#define ROC_GEMM_PATH_SIMT 2
+int roc_last_gemm_path(int which);
+
 /* ------------------------------------------------------------ optimizer --- */
 
 /* Replaces adam_update, optimizer_kernel.cu:43-63 (launch :98-101).  alpha_t is

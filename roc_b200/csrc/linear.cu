@@ -34,6 +34,10 @@ static bool force_simt() {
   if (v < 0) { const char* e = getenv("ROC_B200_GEMM"); v = (e && e[0] == 's' && e[1] == 'i') ? 1 : 0; }
   return v == 1;
 }
+// which kernel family served the calling thread's last Linear GEMM of each kind (test hook: the tensor-core path
+// returns ROC_ERR_UNSUPPORTED for shapes it does not take and the dispatcher then uses SIMT — a test that means to
+// check tcgen05 must be able to see that it did)
+static thread_local int t_lastPath[3] = {0, 0, 0};   // fwd, dW, dX: 0 none, 1 tcgen05, 2 SIMT
 }  // namespace roc
 
 using namespace roc;
@@ -60,8 +64,9 @@ static int linear_fwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
   const int relu = activation == ROC_AC_MODE_RELU;
   if (!force_simt()) {
     int rc = tc_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, dm, as_stream(stream));
-    if (rc != ROC_ERR_UNSUPPORTED) return rc;
+    if (rc != ROC_ERR_UNSUPPORTED) { t_lastPath[0] = 1; return rc; }
   }
+  t_lastPath[0] = 2;
   return simt_linear_fwd(rows, inDim, outDim, X, ldX, W, Y, ldY, relu, re, colLeft, dm, as_stream(stream));
 }
 
@@ -116,6 +121,8 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
     rc = ROC_ERR_UNSUPPORTED;
     if (!force_simt())
       rc = tc_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
+    t_lastPath[1] = 1;
+    if (rc == ROC_ERR_UNSUPPORTED) t_lastPath[1] = 2;
     if (rc == ROC_ERR_UNSUPPORTED)
       rc = simt_linear_dw(rows, inDim, outDim, X, ldX, dY, ldDY, dW, (float*)workspace, workspaceBytes, dm, st);
     if (rc != ROC_OK) return rc;
@@ -125,6 +132,8 @@ static int linear_bwd_impl(int64_t rows, int inDim, int outDim, const float* X, 
     if (!force_simt())
       rc = tc_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, dxReluOf, ldReluOf, dxRowEnd,
                         colLeft, st);
+    t_lastPath[2] = 1;
+    if (rc == ROC_ERR_UNSUPPORTED) t_lastPath[2] = 2;
     if (rc == ROC_ERR_UNSUPPORTED)
       rc = simt_linear_dx(rows, inDim, outDim, dY, ldDY, W, dX, ldDX, accumulate_dX, dm, dxReluOf, ldReluOf, dxRowEnd,
                           colLeft, st);
@@ -166,3 +175,5 @@ extern "C" int roc_linear_bwd_fused(const roc_linear_bwd_args* a, roc_stream_t s
                          a->dX, a->ldDX, a->activation, a->accumulate_dX, a->workspace, a->workspaceBytes, use,
                          a->dxReluOf, a->ldReluOf, a->dxNormRowEnd, a->colLeft, stream, a->parts);
 }
+
+extern "C" int roc_last_gemm_path(int which) { return (which >= 0 && which < 3) ? t_lastPath[which] : 0; }

@@ -3,6 +3,7 @@ inputs, against the golden vectors minted from the reference's kernels, and (whe
 oracle/_ref is present) against the reference kernels run side by side.
 Bit-exact for indices / masks / partition bounds; 1e-4 relative for fp32 tensors."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -499,3 +500,56 @@ def test_side_by_side_with_reference_kernel():
         got = plan.forward(x)
         torch.cuda.synchronize()
         rel_close(got.cpu().numpy(), want.cpu().numpy(), what="vs live aggre_coop_kernel H=%d" % h)
+
+
+# ---------------------------------------- tcgen05 Linear vs the reference library at the headline shapes ---
+LIN_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_linear.npz")
+
+
+def _lin_inputs(n, i, o):
+    r = np.random.RandomState(1000 * i + o)        # tests/golden/make_golden_linear.py
+    return (r.rand(n, i).astype(np.float32) * 2 - 1, r.rand(o, i).astype(np.float32) * 2 - 1,
+            r.rand(n, o).astype(np.float32) * 2 - 1)
+
+
+@pytest.mark.parametrize("n,i,o", [(1000, 602, 64), (1000, 64, 41)])
+def test_tcgen05_linear_meets_the_reference_cublas(n, i, o):
+    """BASELINE.json configs[1]'s two Linear shapes, fed row-padded so the tcgen05 / TMEM kernels run (asserted
+    through roc_last_gemm_path) — against outputs of the REFERENCE's cublasSgemm calls (linear_kernel.cu:76-80,
+    220-231) minted on a B200 by tests/golden/make_golden_linear.py, and live against oracle/_ref when it is there."""
+    X, W, dY = _lin_inputs(n, i, o)
+    xp = K.padded(n, i, DEV, fill=torch.from_numpy(X).to(DEV))
+    w = torch.from_numpy(W).to(DEV)
+    gyp = K.padded(n, o, DEV, fill=torch.from_numpy(dY).to(DEV))
+    y = K.linear_fwd(xp, w)
+    assert _lib.lib.roc_last_gemm_path(0) == 1, "forward did not take the tcgen05 path"
+    dw = torch.zeros_like(w)
+    dx = K.padded(n, i, DEV)
+    K.linear_bwd(xp, w, None, gyp, dw, dx, activation=0)
+    assert _lib.lib.roc_last_gemm_path(1) == 1 and _lib.lib.roc_last_gemm_path(2) == 1, "dW / dX not on tcgen05"
+    torch.cuda.synchronize()
+    k = "%dx%dx%d" % (n, i, o)
+    wants = []
+    if os.path.exists(LIN_GOLDEN):
+        g = np.load(LIN_GOLDEN)
+        wants.append(("golden", g["Y_" + k], g["dW_" + k], g["dX_" + k]))
+    if ref.available():
+        xd, gyd = torch.from_numpy(X).to(DEV), torch.from_numpy(dY).to(DEV)
+        ry = ref.linear_fwd(xd, w, relu=False)
+        rw, rx = torch.zeros_like(w), torch.zeros_like(xd)
+        ref.linear_bwd(xd, w, ry, gyd.clone(), rw, rx, relu=False)
+        torch.cuda.synchronize()
+        wants.append(("live reference", ry.cpu().numpy(), rw.cpu().numpy(), rx.cpu().numpy()))
+    if not wants:
+        pytest.skip("neither tests/golden/ref_golden_linear.npz nor oracle/_ref is present")
+    for name, wy, wdw, wdx in wants:
+        rel_close(y.cpu().numpy(), wy, what="Y vs %s" % name)
+        rel_close(dw.cpu().numpy(), wdw, what="dW vs %s" % name)
+        rel_close(dx.cpu().numpy(), wdx, what="dX vs %s" % name)
+
+
+def test_unpadded_linear_reports_the_simt_fallback():
+    x = torch.rand((200, 33), device=DEV)            # ld = 33: not 16-byte rows -> the tensor-core kernels decline
+    w = torch.rand((9, 33), device=DEV)
+    K.linear_fwd(x, w, out=torch.empty((200, 9), device=DEV))
+    assert _lib.lib.roc_last_gemm_path(0) == 2

@@ -12,9 +12,10 @@ import pytest
 import torch
 
 from conftest import ROOT, rel_close
+from witness import torch_witness
 from oracle import oracle
 from roc_b200 import _lib, datasets
-from roc_b200.model import Host, Model, build_gcn
+from roc_b200.model import Host, Model, build_gcn, build_sage_mean
 
 pytestmark = pytest.mark.gpu
 
@@ -179,3 +180,57 @@ def test_file_loaders_and_driver(tmp_path):
     assert np.array_equal(np.fromfile(prefix2 + ".feats.bin", dtype=np.float32).reshape(feats.shape), feats)
     lines = [l for l in p.stderr.splitlines() if "[INFER]" in l]
     assert len(lines) == 2 and "train_accuracy" in lines[0]      # epochs 0 and 5 (gnn.cc:107-110)
+
+
+def test_cfg5_shape_residual_wide_hidden_dense_graph():
+    """BASELINE.json configs[4] at a reduced size: 4 layers + the residual branch (5 dims), hidden 256 (the TMA
+    ring ScatterGather variant), dropout, on a graph whose every row is cut at chunk boundaries (mean degree
+    ~150: carries + fix-up on every row)."""
+    layers = (40, 256, 256, 256, 9)
+    re_t, col_t = datasets.powerlaw_graph(600, 60000, seed=4)
+    row_end, col = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
+    feats, labels, mask = datasets.node_data(600, layers[0], layers[-1], seed=2)
+    case = (row_end, col, feats.numpy(), labels.numpy(), mask.numpy())
+    epochs = 2
+    got = run_product(*case, layers, 0.5, epochs, True)
+    want = run_oracle(*case, layers, 0.5, epochs, got["w0"], relu_masks=got["relu_masks"])
+    assert want["flips"] <= 8
+    rel_close(got["logits"], want["logits"], what="logits epoch 0")
+    for p, (a, b) in enumerate(zip(got["dW"], want["dW"])):
+        rel_close(a, b, rtol=2e-4, what="dW[%d] epoch 0" % p)
+    for ep in range(epochs):
+        assert got["perf"][ep]["trainAll"] == want["perf"][ep]["trainAll"]
+        assert abs(got["perf"][ep]["trainLoss"] - want["perf"][ep]["trainLoss"]) <= 2e-4 * abs(want["perf"][ep]["trainLoss"])
+
+
+@pytest.mark.parametrize("kind,layers", [("gcn", (12, 16, 5)), ("gcn", (12, 24, 16, 5)), ("sage", (12, 24, 16, 5))])
+def test_torch_autograd_fp64_witness(kind, layers):
+    re_t, col_t = datasets.rmat_graph(8, 1500, seed=31)
+    row_end, col = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
+    n = row_end.shape[0]
+    feats, labels, mask = datasets.node_data(n, layers[0], layers[-1], seed=9)
+    feats, labels, mask = feats.numpy(), labels.numpy(), mask.numpy()
+    host = Host(0, 0, 1)
+    host.graph_from_arrays(row_end, col)
+    m = Model(host, seed=1)
+    h = (build_gcn if kind == "gcn" else build_sage_mean)(m, list(layers), 0.0)
+    m.set_tensor(h["input"], feats)
+    m.set_labels(h["label"], labels)
+    m.set_tensor(h["mask"], mask.astype(np.int32))
+    w0 = [m.get_parameter(p) for p in range(m.num_parameters())]
+    m.train_mode(); m.zero_gradients(); m.forward()
+    logits = m.get_tensor(h["logits"])
+    m.backward()
+    dw = [m.get_parameter(p, "grad") for p in range(m.num_parameters())]
+    host.close()
+    wl, wdw = torch_witness(kind, row_end, col, feats, labels, mask, layers, w0)
+    rel_close(logits, wl, what="%s logits vs torch fp64" % kind)
+    for p, (a, b) in enumerate(zip(dw, wdw)):
+        rel_close(a, b, rtol=2e-4, atol_scale=2e-5, what="%s dW[%d] vs torch autograd" % (kind, p))
+    if kind == "gcn":   # and the oracle's hand-derived backward against the same witness
+        o = oracle.GcnOracle(row_end, col, layers, w0, dropout=0.0)
+        o.forward(feats, train=True)
+        o.backward(datasets.onehot(labels, layers[-1]), mask)
+        rel_close(o.logits, wl, what="oracle logits vs torch fp64")
+        for p, (a, b) in enumerate(zip(o.dW, wdw)):
+            rel_close(a, b, rtol=1e-4, atol_scale=2e-5, what="oracle dW[%d] vs torch autograd" % p)

@@ -237,3 +237,30 @@ def test_oracle_vs_reference_library_ops(golden):
     rel_close(m, g["adam_m_out"], rtol=1e-5, what="adam m")
     rel_close(v, g["adam_v_out"], rtol=1e-5, what="adam v")
     assert np.array_equal(g["act_x"] + g["act_dy"], g["add_out"])
+
+
+@pytest.mark.parametrize("layers", [(12, 16, 5), (12, 24, 16, 5)])
+def test_gcn_oracle_backward_against_torch_autograd(layers):
+    """GcnOracle's forward and its hand-derived backward (oracle.py, mirroring Model::backward's op order and the
+    first-writer rule) against torch fp64 autograd of the same composition — the goldens pin kernels, this pins
+    the wiring (with and without the residual branch)."""
+    import torch  # noqa: F401
+    from witness import torch_witness
+    from roc_b200 import datasets
+    re_t, col_t = datasets.rmat_graph(8, 1500, seed=31)
+    row_end, col = re_t.numpy().astype(np.uint64), col_t.numpy().astype(np.uint32)
+    n = row_end.shape[0]
+    feats, labels, mask = datasets.node_data(n, layers[0], layers[-1], seed=9)
+    feats, labels, mask = feats.numpy(), labels.numpy(), mask.numpy()
+    r = np.random.RandomState(3)
+    dims = list(zip(layers[:-1], layers[1:]))
+    if len(layers) > 3:
+        dims = [d for d in dims for _ in (0, 1)]
+    w0 = [(r.rand(o, i).astype(np.float32) * 2 - 1) * np.float32(np.sqrt(6.0 / (i + o))) for (i, o) in dims]
+    o = oracle.GcnOracle(row_end, col, layers, w0, dropout=0.0)
+    o.forward(feats, train=True)
+    o.backward(datasets.onehot(labels, layers[-1]), mask)
+    wl, wdw = torch_witness("gcn", row_end, col, feats, labels, mask, layers, w0)
+    assert np.allclose(o.logits, wl, rtol=1e-4, atol=1e-5 * np.abs(wl).max())
+    for a, b in zip(o.dW, wdw):
+        assert np.allclose(a, b, rtol=1e-4, atol=2e-5 * np.abs(b).max())
