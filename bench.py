@@ -133,6 +133,7 @@ def make_graph(ds, cfg, world, device, scale_override=0):
     import torch
     t0 = time.time()
     g = CONFIGS[cfg]["graph"]
+    shrink = (1 << (BASE_SCALE - scale_override)) if scale_override else 1     # --scale also shrinks the fixed-size graphs (debug)
     if g == "uniform":
         row_end, col = ds.uniform_graph(1000, 4500, seed=1, device=device)
         label = "uniform 1K/10K"
@@ -144,11 +145,11 @@ def make_graph(ds, cfg, world, device, scale_override=0):
         row_end, col = ds.rmat_graph(scale, pairs, seed=1, device=device)
         label = "R-MAT scale-%d" % scale
     elif g == "products":      # configs[2]: 2.45M vertices, ~62M edges
-        row_end, col = ds.powerlaw_graph(2449029, 30_000_000, alpha=1.6, seed=1, device=device)
-        label = "products-shaped"
+        row_end, col = ds.powerlaw_graph(2449029 // shrink, 30_000_000 // shrink, alpha=1.6, seed=1, device=device)
+        label = "products-shaped" + (" / %d" % shrink if shrink > 1 else "")
     elif g == "reddit":        # configs[4]: 233K vertices, ~115M edges (mean degree ~490)
-        row_end, col = ds.powerlaw_graph(232965, 57_500_000, alpha=1.3, seed=1, device=device)
-        label = "Reddit-shaped"
+        row_end, col = ds.powerlaw_graph(232965 // shrink, 57_500_000 // shrink, alpha=1.3, seed=1, device=device)
+        label = "Reddit-shaped" + (" / %d" % shrink if shrink > 1 else "")
     else:
         raise KeyError(g)
     if device != "cpu":
@@ -358,6 +359,7 @@ def run_ours(args, rank, local_rank, world):
         m.set_labels(hnd["label"], labels.numpy())
         m.set_tensor_from_host_ptr(hnd["mask"], mask.data_ptr())
     upload()
+    log("[bench] model built, inputs uploaded")
     h2d = feats.numel() * 4 + labels.numel() * 4 + mask.numel() * 4
     d2h = 28   # sizeof(PerfMetrics)
 
@@ -400,6 +402,8 @@ def run_ours(args, rank, local_rank, world):
     # ---- resident-in-HBM arm
     for _ in range(max(args.warmup, 3)):
         m.train_epoch()
+    host.synchronize()
+    log("[bench] warm-up done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -107,6 +107,7 @@ struct RuntimeImpl {
   // steps and printed by rank 0 when the Runtime goes away (where does a step's time go at N GPUs?)
   struct OpTiming { int layer; int dir; cudaEvent_t a, b; };
   bool opProf = false;
+  bool opTrace = false;
   std::vector<OpTiming> opTimings;
   std::vector<std::string> opNames;
   void op_begin(int layer, int dir);

@@ -145,6 +145,11 @@ void RuntimeImpl::sg_end() {
 }
 
 void RuntimeImpl::op_begin(int layer, int dir) {
+  if (opTrace) {   // ROC_B200_TRACE=1: name every op before it runs and synchronise after it (which op hangs / faults?)
+    fprintf(stderr, "[roc_b200 trace] part %d %s layer %d %s ...\n", myPart, dir == 0 ? "fwd" : (dir == 1 ? "bwd" : "upd"), layer,
+            (layer >= 0 && (size_t)layer < opNames.size()) ? opNames[(size_t)layer].c_str() : "-");
+    fflush(stderr);
+  }
   if (!opProf) return;
   OpTiming t; t.layer = layer; t.dir = dir;
   ROC_CHECK(cudaEventCreate(&t.a)); ROC_CHECK(cudaEventCreate(&t.b));
@@ -152,6 +157,11 @@ void RuntimeImpl::op_begin(int layer, int dir) {
   opTimings.push_back(t);
 }
 void RuntimeImpl::op_end() {
+  if (opTrace) {
+    cudaError_t e = cudaStreamSynchronize(stream);
+    fprintf(stderr, "[roc_b200 trace] part %d    done (%s)\n", myPart, cudaGetErrorString(e));
+    fflush(stderr);
+  }
   if (!opProf || opTimings.empty()) return;
   ROC_CHECK(cudaEventRecord(opTimings.back().b, stream));
 }
@@ -362,7 +372,19 @@ Runtime::Runtime(int device, int myPart, int numParts) {
   ROC_CHECK(cudaMemsetAsync(impl->d_barrier, 0, sizeof(int), impl->stream));
   if (const char* e = getenv("ROC_B200_PUSH_SMS")) impl->pushSMs = std::max(0, atoi(e));
   if (const char* e = getenv("ROC_B200_OPPROF")) impl->opProf = e[0] == '1';
+  if (const char* e = getenv("ROC_B200_TRACE")) impl->opTrace = e[0] == '1';
   if (const char* e = getenv("ROC_B200_PUSH_GRID")) impl->pushGridSMs = atoi(e);   // experiments: SMs the pipelined push grid is sized for (0 = chip)
+  {
+    // The stream-ordered allocations of the kernel layer (the GEMMs' split-weight scratch) come from the device's
+    // default pool; by default it hands unused memory back at every synchronisation and the next step pays the
+    // driver allocation again (one 35 ms step among ten 18.7 ms ones, r2 session 1).  Keep it.
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   impl->d_perf = (roc_perf_metrics*)impl->dmalloc(sizeof(roc_perf_metrics));
   ROC_CHECK(cudaMemsetAsync(impl->d_perf, 0, sizeof(roc_perf_metrics), impl->stream));
 }
