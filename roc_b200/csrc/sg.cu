@@ -684,7 +684,44 @@ sg_chunk_kernel_t(const SgParams p, const __grid_constant__ CUtensorMap tmap) {
   const char* inB = reinterpret_cast<const char*>(p.in);
   const uint32_t strideB = (uint32_t)p.ldIn * 16u;
   const uint32_t rowB = p.Q * 16u;
+  // MODE 2: the source ids never sit in front of the issue.  Lane j of the worker loads, once and up front, the
+  // ids of gather4 units j, j + L, ... of the worker's edge range (a worker has at most 127 edges = 32 units) and
+  // issues those units itself when their ring slot frees (ncu on MODE 0: 21 % of the stall samples waited for the
+  // id load of the stage about to be issued).
+  constexpr int NU = (MODE == 2) ? (32 / L) : 1;
+  uint4 ids[NU];
+  if (MODE == 2 && nE) {
+#pragma unroll
+    for (int n = 0; n < NU; n++) {
+      const uint32_t e4 = 4u * ((uint32_t)lane + (uint32_t)n * L);
+      const uint32_t last = nE - 1u;
+      const uint32_t* cp = col + eb;
+      ids[n] = make_uint4(__ldg(cp + min(e4, last)), __ldg(cp + min(e4 + 1u, last)), __ldg(cp + min(e4 + 2u, last)),
+                          __ldg(cp + min(e4 + 3u, last)));
+    }
+  }
   auto issue = [&](uint32_t k, uint32_t slot) {
+    if (MODE == 2) {
+      if (k < nStages) {
+        const uint32_t off = k * G;
+        const uint32_t bar = bars + slot * 8;
+        const uint32_t dst = ring + slot * STAGEB;
+        const uint32_t nv = min((uint32_t)G, nE - off);
+        const uint32_t n4 = (nv + 3u) >> 2;
+        if ((uint32_t)lane == (k * S) % (uint32_t)L) mbar_expect_tx_a(bar, n4 * G4B);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+          const uint32_t g = k * S + (uint32_t)s;              // gather4 unit within the worker's range
+          if ((uint32_t)s < n4 && (uint32_t)lane == g % (uint32_t)L) {
+            uint4 id = ids[0];
+#pragma unroll
+            for (int n = 1; n < NU; n++) if (g / (uint32_t)L == (uint32_t)n) id = ids[n];
+            tma_gather4(dst + s * G4B, &tmap, 0, id.x, id.y, id.z, id.w, bar);
+          }
+        }
+      }
+      return;
+    }
     if (k < nStages && lane == 0) {
       const uint32_t off = k * G;
       const uint32_t* cp = col + eb + off;
@@ -1123,7 +1160,7 @@ sg_fixup_big_kernel(const SgParams p) {
 static int sg_variant_env() {   // -1 default, 0 = A, 2 = C, 3 = T (TMA gather4), 4 = T with per-row bulk copies, 5 = R (ring)
   const char* e = getenv("ROC_SG_VARIANT");   // re-read per call: the kernel bench switches it in-process
   if (!e) return -1;
-  switch (e[0]) { case 'a': return 0; case 'c': return 2; case 't': return 3; case 'b': return 4; case 'r': return 5; default: return -1; }
+  switch (e[0]) { case 'a': return 0; case 'c': return 2; case 't': return 3; case 'b': return 4; case 'r': return 5; case 'u': return 6; default: return -1; }
 }
 static int sg_deep_env() {   // ROC_SG_DEEP=1: variant C with a 2x deeper ring (experiments)
   const char* e = getenv("ROC_SG_DEEP");
@@ -1219,6 +1256,7 @@ static cudaError_t launch_t_cfg(const SgParams& p, const CUtensorMap& tm, int cf
       default: return launch_t<L, NCH, 1, 4, 128, 6, MODE>(p, tm, st);
     }
   } else if constexpr (NCH == 1) {        // 512 B rows, one worker per warp
+    if (cfg < 0 && MODE == 2) cfg = 1;     // ids held by the lanes: two 8-edge stages (3.18 ms vs 5.45 with four 4-edge ones)
     switch (cfg) {
       case 1: return launch_t<L, NCH, 2, 2, 128, 4, MODE>(p, tm, st);
       case 2: return launch_t<L, NCH, 1, 8, 128, 3, MODE>(p, tm, st);
@@ -1261,6 +1299,14 @@ static int launch_cfg(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
     if constexpr (VEC == 4 && NCH <= 2 && L >= 16) {
       if (variant == 5) {
         cudaError_t e = launch_r_cfg(p, *how.tmap, how.tcfg, st);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        done = true;
+      }
+    }
+    if constexpr (VEC == 4 && NCH <= 2 && L >= 16) {
+      if (variant == 6) {
+        cudaError_t e = launch_t_cfg<L, NCH, 2>(p, *how.tmap, how.tcfg, st);
         if (e != cudaSuccess) return (int)e;
         count_launch();
         done = true;
@@ -1318,11 +1364,12 @@ static int dispatch(const SgParams& p, const SgLaunch& how, cudaStream_t st) {
 static int pick_variant(uint32_t Q, bool vec) {
   int v = sg_variant_env();
   if (!vec) return 0;
-  // measured on R-MAT-22 (r2 runs 2 / 6 / 8, ms at H = 64 / 128 / 256): A 1.91 / 3.55 / 7.9, C 2.65 / 4.40 / 7.8,
-  // T 2.11 / 3.61 / 7.08, R 2.43 / 4.5 / 15.3 -> registers up to 128 floats, the TMA ring for 129..256
-  if (v < 0) v = (Q > 64) ? 2 : (Q > 32 ? 3 : 0);
-  if ((v == 3 || v == 4 || v == 5) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
-  if (v == 5 && Q <= 8) v = 0;                            // the ring kernel wants rows of 9+ float4
+  // measured on R-MAT-22 (r2 runs 2 / 6 / 8 and session 5, ms at H = 64 / 128 / 256): A 1.91 / 3.55 / 7.9,
+  // C 2.65 / 4.40 / 7.8, T 2.11 / 3.42 / 7.08, T with lane-held ids (U) 2.20 / 3.18 / 6.77, R 2.43 / 4.5 / 15.3
+  // -> registers up to 64 floats, the TMA gather4 ring with lane-held ids for 65..256
+  if (v < 0) v = (Q > 64) ? 2 : (Q > 16 ? 6 : 0);
+  if ((v == 3 || v == 4 || v == 5 || v == 6) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
+  if ((v == 5 || v == 6) && Q <= 8) v = 0;                // these want rows of 9+ float4
   return v;
 }
 
@@ -1462,8 +1509,8 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
   // column blocks: the widest kernel covers 256 T-columns (1024 floats vectorised, 256 scalar);
   // the TMA variants take 64 T-columns (a tensor-map box is at most 256 elements wide)
   int variant = pick_variant(vec ? ((uint32_t)H + 3) / 4 : (uint32_t)H, vec);
-  if ((variant == 3 || variant == 4 || variant == 5) && H > 256 && sg_variant_env() < 0) variant = 2;
-  const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4 || variant == 5) ? 256 : 1024);
+  if ((variant == 3 || variant == 4 || variant == 5 || variant == 6) && H > 256 && sg_variant_env() < 0) variant = 2;
+  const int blockCols = !vec ? 256 : ((variant == 3 || variant == 4 || variant == 5 || variant == 6) ? 256 : 1024);
   {
     int need = H < blockCols ? H : blockCols;
     int rc = ensure_carry(pl, ((size_t)need + 3) / 4 * 4, st, true);
@@ -1487,7 +1534,7 @@ extern "C" int roc_sg_forward_planned(const roc_sg_plan* plc, int H, const float
       p.ldIn = (size_t)ldIn / 4; p.ldOut = (size_t)ldOut / 4; p.ldC = pl->carryLd / 4;
       p.Q = ((uint32_t)hb + 3) / 4;
       if (variant == 5 && (!aligned16(pl->col) || p.Q <= 8)) how.variant = 0;   // producer reads col as uint4
-      if (variant == 3 || how.variant == 5) {
+      if (variant == 3 || variant == 6 || how.variant == 5) {
         // tensor map of the input: [inRows][Q*4] floats, rows ldIn floats apart; the box is the worker's
         // whole lane span (columns past Q*4 are zero-filled), one row per box — gather4 fetches four
         const uint32_t span = p.Q <= 4 ? 4u : p.Q <= 8 ? 8u : p.Q <= 16 ? 16u : p.Q <= 32 ? 32u : 64u;

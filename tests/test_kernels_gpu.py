@@ -80,7 +80,8 @@ def test_sg_variants_are_bitwise_identical(kind, h, monkeypatch):
     base = plan.forward(xp).clone()
     base_e = plan.forward(xp, epilogue=_lib.SG_EPI_NORM | _lib.SG_EPI_RELU).clone()
     rel_close(base.cpu().numpy(), oracle.scatter_gather(0, n - 1, 0, row_end, col, x), what="A %s H=%d" % (kind, h))
-    for variant, cfgs in (("c", [None]), ("r", [None, 1, 4]), ("t", [None, 1, 2, 3, 4, 5, 6]), ("b", [None, 1, 3])):
+    for variant, cfgs in (("c", [None]), ("r", [None, 1, 4]), ("t", [None, 1, 2, 3, 4, 5, 6]), ("u", [None, 1, 2, 3]),
+                          ("b", [None, 1, 3])):
         monkeypatch.setenv("ROC_SG_VARIANT", variant)
         for cfg in cfgs:
             if cfg is None:
