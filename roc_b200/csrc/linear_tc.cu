@@ -462,11 +462,13 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   { const char* g = getenv("ROC_B200_GEMM"); if (g && g[0] == 'n' && g[1] == 'o') return ROC_ERR_UNSUPPORTED; }   // "notc"
   int BN = (N + 15) / 16 * 16;
   if (BN > 128) BN = 128;
-  // Known limitation (r2 session 3): the 128-column tile with a long K (602 -> 19 k-blocks, 4 stages) stops making
-  // progress on the 4.2 M-row input of configs[3] (32 K row tiles; 2 K tiles are fine, and so are 128-column tiles
-  // with K <= 256 at 19 K row tiles).  Until that is root-caused, long-K products take 64-column tiles — the shape
-  // every headline number was measured on — at the price of streaming A once per 64 output columns.
-  if (BN > 64 && K > 256) BN = 64;
+  // Known limitation (r2 sessions 1, 3, 6): with 128-column output tiles the kernel occasionally stops making progress
+  // — every time on the 4.2 M-row 602 -> 128 product of configs[3] (19 k-blocks, 32 K row tiles), and in two of four
+  // runs of configs[2] (N = 256, K <= 256) after a few steps; never seen with tiles of up to 64 columns, the shape
+  // every headline number and every parity test runs on.  Until the 128-column path is root-caused (the second
+  // accumulator's hand-over is the suspect: it is the only structure whose size changes), all products take 64-column
+  // tiles and stream A once per 64 output columns.
+  if (BN > 64) BN = 64;
   const int nTiles = (N + BN - 1) / BN;
   const int Npad = nTiles * BN;
   const int Kpad = (K + TC_BK - 1) / TC_BK * TC_BK;

@@ -1366,8 +1366,8 @@ static int pick_variant(uint32_t Q, bool vec) {
   if (!vec) return 0;
   // measured on R-MAT-22 (r2 runs 2 / 6 / 8 and session 5, ms at H = 64 / 128 / 256): A 1.91 / 3.55 / 7.9,
   // C 2.65 / 4.40 / 7.8, T 2.11 / 3.42 / 7.08, T with lane-held ids (U) 2.20 / 3.18 / 6.77, R 2.43 / 4.5 / 15.3
-  // -> registers up to 64 floats, the TMA gather4 ring with lane-held ids for 65..256
-  if (v < 0) v = (Q > 64) ? 2 : (Q > 16 ? 6 : 0);
+  // -> registers up to 64 floats, the TMA gather4 ring with lane-held ids for 65..128, with per-stage ids for 129..256
+  if (v < 0) v = (Q > 64) ? 2 : (Q > 32 ? 3 : (Q > 16 ? 6 : 0));   // 129..256: U's 4 % over T not worth a less exercised path
   if ((v == 3 || v == 4 || v == 5 || v == 6) && Q > 64) v = 2;     // TMA boxes are at most 256 elements wide
   if ((v == 5 || v == 6) && Q <= 8) v = 0;                // these want rows of 9+ float4
   return v;
