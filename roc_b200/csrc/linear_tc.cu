@@ -462,13 +462,14 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   { const char* g = getenv("ROC_B200_GEMM"); if (g && g[0] == 'n' && g[1] == 'o') return ROC_ERR_UNSUPPORTED; }   // "notc"
   int BN = (N + 15) / 16 * 16;
   if (BN > 128) BN = 128;
-  // Known limitation (r2 sessions 1, 3, 6): with 128-column output tiles the kernel occasionally stops making progress
-  // — every time on the 4.2 M-row 602 -> 128 product of configs[3] (19 k-blocks, 32 K row tiles), and in two of four
-  // runs of configs[2] (N = 256, K <= 256) after a few steps; never seen with tiles of up to 64 columns, the shape
-  // every headline number and every parity test runs on.  Until the 128-column path is root-caused (the second
-  // accumulator's hand-over is the suspect: it is the only structure whose size changes), all products take 64-column
-  // tiles and stream A once per 64 output columns.
-  if (BN > 64) BN = 64;
+  // 128-column tiles leave room for only 3 stages; with two split groups taking alternate k-blocks a group then met
+  // a stage's `full` barrier only every other phase, and a parity wait that skipped a phase takes the stale
+  // completion for its own: sporadic hangs (every time on the 4.2 M-row 602 -> 128 product of configs[3]; two of four
+  // runs of configs[2]; r2 sessions 1 / 3 / 6).  Fixed below (one split group whenever the stage count is odd), but
+  // that build has seen a GPU only through ROC_TS_BN128=1 runs: until it has more mileage, products take the
+  // 64-column tiles every headline number and parity test runs on and stream A once per 64 output columns
+  // (measured cost on configs 2-4: within +-1.5 %).
+  { const char* e = getenv("ROC_TS_BN128"); if (BN > 64 && !(e && e[0] == '1')) BN = 64; }
   const int nTiles = (N + BN - 1) / BN;
   const int Npad = nTiles * BN;
   const int Kpad = (K + TC_BK - 1) / TC_BK * TC_BK;
@@ -492,21 +493,38 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   // 2 accumulators of dStride columns + `stages` A slots of 64 columns in the 512 TMEM columns
   const uint32_t dStride = (uint32_t)((BN + 31) / 32 * 32);
   const size_t stageBytes = (size_t)TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
-  int stages = (int)((512 - 2 * dStride) / 64);
-  if (stages > TS_MAX_STAGES) stages = TS_MAX_STAGES;
-  const size_t fixedBytes = 1024 /*align*/ + 256 /*barriers*/ + (size_t)8 * EPI_STG_FLOATS * sizeof(float);
-  while (stages > 0 && (size_t)stages * stageBytes + fixedBytes > (size_t)224 * 1024) stages--;
+  // Warp roles first (they size the epilogue staging), then the stage count.
+  // Few k-blocks per tile (K <= 128): the epilogue, not the main loop, paces the kernel -> 8 epilogue warps and one
+  // split group; otherwise two split groups (alternate k-blocks) and 4 epilogue warps.  512 threads either way.
+  int epiStaged = 1;
+  { const char* ee = getenv("ROC_TS_EPI"); if (ee) epiStaged = (ee[0] == 's'); }
+  int splitGroups = (Kpad / TC_BK <= 4 && epiStaged) ? 1 : 2;
+  { const char* s2 = getenv("ROC_TS_SPLIT"); if (s2) splitGroups = (s2[0] == '1') ? 1 : 2; }
+  if (!epiStaged) splitGroups = 2;
+  int stages = 0;
+  size_t fixedBytes = 0;
+  for (;;) {
+    const int epiWarps = 12 - 4 * splitGroups;
+    fixedBytes = 1024 /*align*/ + 256 /*barriers*/ + (size_t)epiWarps * EPI_STG_FLOATS * sizeof(float);
+    stages = (int)((512 - 2 * dStride) / 64);
+    if (stages > TS_MAX_STAGES) stages = TS_MAX_STAGES;
+    while (stages > 0 && (size_t)stages * stageBytes + fixedBytes > (size_t)224 * 1024) stages--;
+    // Two split groups take alternate k-blocks, i.e. alternate stages: with an EVEN stage count each group owns its
+    // stages and meets every phase of their barriers.  With an odd count a group would meet a stage's `full` barrier
+    // only every other phase, and an mbarrier parity wait that skipped a phase takes the stale completion for its
+    // own (3 stages: sporadic hangs of the 128-column tiles, r2 sessions 1 / 3 / 6; 5 stages — what the 64-column
+    // tiles ran with before the staging was sized by the warp roles — left two loads of slack and never tripped).
+    if (splitGroups == 2 && (stages & 1)) stages--;
+    if (stages >= 3 || splitGroups == 1) break;
+    splitGroups = 1;                       // not enough room for an even ring of >= 4: one group, any stage count
+  }
   if (stages < 3) return ROC_ERR_UNSUPPORTED;
   TcTsParams q{};
   q.Y = Y; q.ldY = ldY; q.rows = rows; q.outDim = N; q.BN = BN; q.numKb = Kpad / TC_BK;
   q.stages = stages; q.tmemCols = 512; q.dStride = dStride; q.aCol0 = 2 * dStride;
   q.accumulate = e.accumulate;
-  { const char* ee = getenv("ROC_TS_EPI"); q.epiStaged = ee ? (ee[0] == 's') : 1; }
-  // few k-blocks per tile (K <= 128): the epilogue, not the main loop, paces the kernel -> 8 epilogue
-  // warps and one split group; otherwise two split groups and 4 epilogue warps.  512 threads either way.
-  q.splitGroups = (Kpad / TC_BK <= 4 && q.epiStaged) ? 1 : 2;
-  { const char* s2 = getenv("ROC_TS_SPLIT"); if (s2) q.splitGroups = (s2[0] == '1') ? 1 : 2; }
-  if (!q.epiStaged) q.splitGroups = 2;
+  q.epiStaged = epiStaged;
+  q.splitGroups = splitGroups;
   q.epiWarps = 12 - 4 * q.splitGroups;
   if (inMask) { q.mask = inMask->bits; q.ldm = inMask->ld; q.mscale = inMask->scale; }
   q.relu = e.relu;

@@ -297,6 +297,12 @@ int tc_linear_dw(int64_t rows, int inDim, int outDim, const float* X, int64_t ld
     t.vPerSplit = ((rows + q.splits - 1) / q.splits + q.KS - 1) / q.KS * q.KS;
     t.tmemCols = 512; t.aCol0 = (uint32_t)q.aCol0;
     { const char* e = getenv("ROC_TS_SPLIT"); t.splitGroups = (e && e[0] == '1') ? 1 : 2; }
+    // Two split groups take alternate A slots (and, with a single M-tile, alternate stages).  With an ODD number of
+    // slots or stages a group then meets the same barrier only every other phase — and an mbarrier parity wait is
+    // only meaningful one phase ahead (a waiter that skipped a phase takes the stale completion for its own).  One
+    // group sees every phase of every barrier.  (Found through the forward kernel's 128-column tiles, which run
+    // with 3 stages: sporadic hangs, r2 sessions 1 / 3 / 6.)
+    if (t.splitGroups == 2 && ((q.stages & 1) || (q.slots & 1))) t.splitGroups = 1;
     CUtensorMap mapM = mapDY;   // placeholder when there is no mask (never dereferenced)
     if (dm) {
       t.mask = dm->bits; t.ldm = dm->ld; t.mscale = dm->scale;
