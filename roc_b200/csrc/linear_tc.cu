@@ -462,14 +462,11 @@ static int ts_gemm(int64_t rows, int K, int N, const float* A, int64_t ldA, cons
   { const char* g = getenv("ROC_B200_GEMM"); if (g && g[0] == 'n' && g[1] == 'o') return ROC_ERR_UNSUPPORTED; }   // "notc"
   int BN = (N + 15) / 16 * 16;
   if (BN > 128) BN = 128;
-  // 128-column tiles leave room for only 3 stages; with two split groups taking alternate k-blocks a group then met
-  // a stage's `full` barrier only every other phase, and a parity wait that skipped a phase takes the stale
-  // completion for its own: sporadic hangs (every time on the 4.2 M-row 602 -> 128 product of configs[3]; two of four
-  // runs of configs[2]; r2 sessions 1 / 3 / 6).  Fixed below (one split group whenever the stage count is odd), but
-  // that build has seen a GPU only through ROC_TS_BN128=1 runs: until it has more mileage, products take the
-  // 64-column tiles every headline number and parity test runs on and stream A once per 64 output columns
-  // (measured cost on configs 2-4: within +-1.5 %).
-  { const char* e = getenv("ROC_TS_BN128"); if (BN > 64 && !(e && e[0] == '1')) BN = 64; }
+  // (128-column tiles hung sporadically in r2 sessions 1 / 3 / 6 — every time on the 4.2 M-row 602 -> 128 product of
+  // configs[3]: the ring had 3 stages and the two split groups met a stage's barrier only every other phase; fixed
+  // below by keeping the stage count even.  Validated on configs 2-4 and the GEMM / model tests in sessions 8 / 9;
+  // ROC_TS_BN128=0 goes back to 64-column tiles, which stream A once per 64 output columns.)
+  { const char* e = getenv("ROC_TS_BN128"); if (BN > 64 && e && e[0] == '0') BN = 64; }
   const int nTiles = (N + BN - 1) / BN;
   const int Npad = nTiles * BN;
   const int Kpad = (K + TC_BK - 1) / TC_BK * TC_BK;
