@@ -117,8 +117,9 @@ typedef struct roc_sg_plan roc_sg_plan;
 int roc_sg_plan_create(roc_vid_t rowLeft, roc_vid_t rowRight, roc_eid_t colLeft,
                        const roc_eid_t* rowEnd, const roc_vid_t* colSrc,
                        roc_stream_t stream, roc_sg_plan** plan);
-/* Pre-size the carry workspace for feature widths up to maxH (otherwise it is
- * grown — with a device synchronisation — by the first call that needs it). */
+/* Pre-size the carry workspace for feature widths up to maxH (otherwise it is grown on the stream of the first
+ * call that needs it, with stream-ordered allocation: no device synchronisation, but the plan must then be used
+ * from that one stream). */
 int roc_sg_plan_reserve(roc_sg_plan* plan, int maxH);
 void roc_sg_plan_destroy(roc_sg_plan* plan);
 /* Introspection for tests / DESIGN.md numbers. */
@@ -130,7 +131,9 @@ int roc_sg_plan_info(const roc_sg_plan* plan, uint64_t* numChunks,
  *   out[v-rowLeft][h] = sum_{e in in(v)} in[colSrc[e]][h],  h < H
  * `in` is indexed by whatever ids colSrc holds (global ids over the whole
  * [N][ldIn] matrix as in scattergather.cc:69-73, or local+halo ids).
- * Deterministic: the per-row summation order is fixed by the plan. */
+ * Deterministic: the per-row summation order is fixed by the plan — and is the same in every kernel variant the
+ * library may pick for a width (registers / cp.async / TMA gather4 rings; ROC_SG_VARIANT forces one), so results
+ * do not depend on the variant either. */
 int roc_sg_forward_planned(const roc_sg_plan* plan, int H, const float* in,
                            int64_t ldIn, float* out, int64_t ldOut, int epilogue,
                            roc_stream_t stream);

@@ -6,23 +6,30 @@
 // float atomics; this is a different algorithm built for HBM3e:
 //
 //  * edge-balanced schedule ("plan"): the partition's edge array is cut into
-//    CH = 64-edge chunks; one WORKER (a group of L = min(32, H/4) lanes) owns
-//    chunk c.  A row is owned by the chunk its first edge lies in.  Rows no
-//    longer than CH are always finished by their owner (so a worker does at
-//    most 2*CH-1 edges); a longer ("heavy") row is cut at chunk boundaries: the
-//    owner stores its raw partial, every later chunk stores its part into a
-//    carry slot and a second small kernel adds partial + carries in chunk
-//    order.  No atomics anywhere => bit-reproducible sums (the reference is not:
-//    smem atomicAdd, scattergather_kernel.cu:66).
-//  * the worker's col indices are loaded coalesced 32 edges at a time and
-//    broadcast with sub-warp shuffles; U independent 16-byte row gathers per
-//    lane are issued back to back regardless of row boundaries (the gathers of
-//    a run of short rows overlap), then accumulated in registers in edge order
-//    with a worker-uniform row-boundary test.
-//  * each lane owns 4 consecutive floats (LDG.128): a warp instruction fetches
-//    32/L full neighbour rows, every 32-byte sector fully used.
+//    CH = 64-edge chunks; one WORKER owns chunk c.  A row is owned by the chunk
+//    its first edge lies in.  Rows no longer than CH are always finished by their
+//    owner (so a worker does at most 2*CH-1 edges); a longer ("heavy") row is cut
+//    at chunk boundaries: the owner stores its raw partial, every later chunk
+//    stores its part into a carry slot and a second small kernel adds partial +
+//    carries in chunk order.  No atomics anywhere => bit-reproducible sums (the
+//    reference is not: smem atomicAdd, scattergather_kernel.cu:66).  The plan also
+//    holds a 32-byte start record per chunk (k_chunk_desc) so a worker begins with
+//    one load instead of a three-deep dependent walk.
 //  * the store applies the ops the model puts right after scatter_gather
 //    (indegree_norm, relu; gnn.cc:83-85) so the N x H result is written once.
+//  * FIVE main kernels share that plan and the per-row summation order — they are
+//    bit-identical to each other — and differ in how the neighbour rows travel:
+//      A  sg_chunk_kernel      registers: L = min(32, H/4) lanes per worker, one LDG.128 per lane and row,
+//                              8 rows in flight per lane (default up to 64 floats per row)
+//      C  sg_chunk_kernel_c2   cp.async (LDGSTS) ring per worker (rows wider than 256 floats)
+//      T  sg_chunk_kernel_t    TMA: one cp.async.bulk.tensor ... tile::gather4 per 4 edges into a shared-memory
+//                              ring per worker, mbarrier completion (default for 129..256 floats)
+//      U  (T, MODE 2)          the same with the source ids held by the lanes that issue them (65..128 floats)
+//      b  (T, MODE 1)          one plain cp.async.bulk per row (measurement only)
+//      R  sg_ring_kernel       producer / consumer ring: producer warps issue gather4s for whole chunks into a
+//                              two-slot ring, two worker warps consume (the structure the measured gather ceilings
+//                              ask for; not yet faster — DESIGN.md §3.1)
+//    The choice per width is by measurement (pick_variant); ROC_SG_VARIANT forces one.
 //
 // Algorithmic bytes per launch: E*(4H+4) + Nloc*(4H+8).
 #include <cub/cub.cuh>
