@@ -234,3 +234,33 @@ def test_torch_autograd_fp64_witness(kind, layers):
         rel_close(o.logits, wl, what="oracle logits vs torch fp64")
         for p, (a, b) in enumerate(zip(o.dW, wdw)):
             rel_close(a, b, rtol=1e-4, atol_scale=2e-5, what="oracle dW[%d] vs torch autograd" % p)
+
+
+def test_oracle_comparison_at_scale_20():
+    """One oracle comparison at a realistic size: R-MAT scale 20 (1 M vertices, ~17 M edges, hub rows of degree
+    > 40 000 that span hundreds of chunks) — ScatterGather with the fused epilogue, then one full training step of a
+    GCN 64-32-16 (forward logits, every dW, loss) against the oracle's fp64-accumulating epoch on the host cores."""
+    import torch
+    from roc_b200 import kernels as K
+    re_t, col_t = datasets.rmat_graph(20, 1 << 23, seed=1, device="cuda")
+    row_end = re_t.cpu().numpy().astype(np.uint64)
+    col = col_t.cpu().numpy().astype(np.uint32)
+    n = row_end.shape[0]
+    # --- the hot kernel
+    x = np.random.RandomState(20).rand(n, 64).astype(np.float32) - 0.5
+    plan = K.SgPlan(0, n - 1, 0, re_t, col_t)
+    got = plan.forward(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = oracle.scatter_gather(0, n - 1, 0, row_end, col, x)
+    rel_close(got, want, what="SG at scale 20")
+    del plan
+    # --- one training step through the Model API
+    layers = (64, 32, 16)
+    feats, labels, mask = datasets.node_data(n, layers[0], layers[-1], seed=4)
+    case = (row_end, col, feats.numpy(), labels.numpy(), mask.numpy())
+    got = run_product(*case, layers, 0.5, 1, True)
+    want = run_oracle(*case, layers, 0.5, 1, got["w0"], relu_masks=got["relu_masks"])
+    rel_close(got["logits"], want["logits"], what="logits at scale 20")
+    for p, (a, b) in enumerate(zip(got["dW"], want["dW"])):
+        rel_close(a, b, rtol=2e-4, what="dW[%d] at scale 20" % p)
+    assert got["perf"][0]["trainAll"] == want["perf"][0]["trainAll"]
+    assert abs(got["perf"][0]["trainLoss"] - want["perf"][0]["trainLoss"]) <= 2e-4 * abs(want["perf"][0]["trainLoss"])
