@@ -264,3 +264,24 @@ def test_gcn_oracle_backward_against_torch_autograd(layers):
     assert np.allclose(o.logits, wl, rtol=1e-4, atol=1e-5 * np.abs(wl).max())
     for a, b in zip(o.dW, wdw):
         assert np.allclose(a, b, rtol=1e-4, atol=2e-5 * np.abs(b).max())
+
+
+@pytest.mark.parametrize("n,i,o", [(1000, 602, 64), (1000, 64, 41)])
+def test_oracle_linear_against_reference_cublas_at_headline_shapes(n, i, o):
+    """The oracle's Linear restatement against outputs of the reference's own cublasSgemm calls
+    (linear_kernel.cu:76-80, 220-231) at BASELINE.json configs[1]'s two shapes — minted on a B200 by
+    tests/golden/make_golden_linear.py (the small 200 x 33 . 9 case lives in ref_golden.npz)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_linear.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_golden_linear.npz not minted")
+    g = np.load(path)
+    r = np.random.RandomState(1000 * i + o)            # the generator's inputs
+    X, W, dY = (r.rand(n, i).astype(np.float32) * 2 - 1, r.rand(o, i).astype(np.float32) * 2 - 1,
+                r.rand(n, o).astype(np.float32) * 2 - 1)
+    k = "%dx%dx%d" % (n, i, o)
+    rel_close(oracle.linear_fwd(X, W), g["Y_" + k], what="oracle Y vs reference cublasSgemm")
+    dw = np.zeros_like(W)
+    dx = oracle.linear_bwd(X, W, None, dY.copy(), dw, need_dx=True)
+    rel_close(dw, g["dW_" + k], what="oracle dW vs reference cublasSgemm")
+    rel_close(dx, g["dX_" + k], what="oracle dX vs reference cublasSgemm")
